@@ -1,0 +1,168 @@
+/* libmgv -- C ABI of the B200-native token hot path of karchkha/MelSpec_GPT_VQVAE.
+ *
+ * The reference has no FFI of its own: its boundary for this path is the Python
+ * nn.Module surface.  The drop-in Python modules in
+ * melspec_gpt_vqvae_b200/ keep that surface and call the entry points below through
+ * ctypes; each entry point cites the reference method it replaces (paths relative to the
+ * reference repo root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise;
+ *     tensors are dense, row-major ("contiguous" in torch terms);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls only
+ *     enqueue work unless documented as synchronising;
+ *   - return value 0 = success, nonzero = error code (MGV_ERR_*); the message is available
+ *     from mgv_last_error() on the calling thread.  Nothing throws or aborts across the ABI;
+ *   - there is no CPU fallback: a missing / non-sm_100 device is MGV_ERR_DEVICE;
+ *   - opaque handles (mgv_gpt_t, mgv_vqvae_t) own packed bf16 weight copies, KV cache and
+ *     workspaces; they are bound to the device that was current at creation and are not
+ *     thread-safe per handle.
+ */
+#ifndef MGV_H_
+#define MGV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGV_VERSION 100 /* 0.1.0 */
+
+enum {
+  MGV_OK = 0,
+  MGV_ERR_INVALID = 1,
+  MGV_ERR_CUDA = 2,
+  MGV_ERR_DEVICE = 3,
+  MGV_ERR_STATE = 4,
+  MGV_ERR_UNSUPPORTED = 5
+};
+
+typedef void* mgv_stream_t;
+
+int mgv_version(void);
+const char* mgv_last_error(void);
+/* MGV_OK iff the current CUDA device is compute capability 10.x (B200). */
+int mgv_device_check(void);
+
+/* ------------------------------------------------------------------ (1) quantiser ---- */
+
+/* VectorQuantizer.forward, index part  (vqvae/big_model_attn_gan.py:19-33).
+ * z_bchw: fp32 (B, C, H*W) -- the encoder output as is (no BHWC permute needed);
+ * codebook: fp32 (K, C) = _embedding.weight;  K <= 128, C in {64,128,192,256};
+ * idx_out: int64 (B*H*W) in (b, h, w) order (= encoding_indices.squeeze(1));
+ * dmin_out: optional fp32 (B*H*W), the winning distance.
+ * Distances are fp32, d = (|x|^2 + |e|^2) - 2<x,e>, every sum a sequential fmaf chain over
+ * the channel index; first index wins ties (torch.argmin).  oracle/vq_oracle.c restates it. */
+int mgv_vq_argmin(const float* z_bchw, const float* codebook, int B, int C, int HW, int K,
+                  int64_t* idx_out, float* dmin_out, mgv_stream_t stream);
+
+/* Rest of VectorQuantizer.forward (:36-54) given the indices: straight-through quantized
+ * (B, C, H*W) BCHW, one-hot encodings (B*H*W, K), loss and perplexity scalars (device
+ * pointers to 1 float).  Any output pointer may be NULL.  workspace: >= 8 + 4*K bytes,
+ * 8-byte aligned. */
+int mgv_vq_finish(const float* z_bchw, const float* codebook, const int64_t* idx, int B, int C, int HW,
+                  int K, float commitment_cost, float* quantized_bchw, float* encodings, float* loss_out,
+                  float* perplexity_out, void* workspace, mgv_stream_t stream);
+
+/* VectorQuantizer.get_codebook_entry (:56-71): out[b, c, p] = codebook[idx[b*HW + p], c]
+ * (HW > 0, shape given) or out[n, c] = codebook[idx[n], c] (HW == 0, shape None).
+ * bad_index_flag: optional device int set to 1 if any index is outside [0, K). */
+int mgv_vq_gather(const int64_t* idx, const float* codebook, int64_t n_vec, int C, int HW, int K,
+                  float* out, int* bad_index_flag, mgv_stream_t stream);
+
+/* ------------------------------------------------------------------ (2) minGPT ------- */
+
+typedef struct mgv_gpt mgv_gpt_t;
+
+typedef struct {
+  int vocab_size;  /* config/config_GPT_vas.py: 128 */
+  int block_size;  /* 266 */
+  int n_layer;     /* 24 */
+  int n_head;      /* 16 */
+  int n_embd;      /* 1024 (n_embd / n_head must be 64) */
+  int class_size;  /* 8; 0 = plain GPT without `embedder` */
+  int n_unmasked;  /* transformer/minGPT.py:67-68 */
+  int head_out;    /* 0 = vocab_size; else GPT(last_linear=...) (:144-149) */
+} mgv_gpt_config;
+
+/* GPT.__init__ / GPTClass.__init__ (transformer/minGPT.py:123-154, :205-207). */
+int mgv_gpt_create(const mgv_gpt_config* cfg, mgv_gpt_t** out);
+int mgv_gpt_destroy(mgv_gpt_t* g);
+
+/* Pack one state_dict tensor (fp32, device) into the handle; `name` is the reference
+ * state_dict key relative to the GPT module ("tok_emb.weight", "pos_emb",
+ * "blocks.3.attn.query.weight", "blocks.3.mlp.0.bias", "ln_f.weight", "head.weight",
+ * "embedder.weight", ...).  "blocks.N.attn.mask" is accepted and ignored.  Linear weights
+ * are converted to bf16 (query/key/value fused into one 3C x C matrix). */
+int mgv_gpt_load_weight(mgv_gpt_t* g, const char* name, const float* src, int64_t numel, mgv_stream_t stream);
+
+/* GPT.forward(idx, embeddings) / GPTClass.forward(idx, token) (:168-199, :209-212),
+ * eval mode (dropout off).  Sequence = m prefix rows + t token rows.
+ *   idx: int64 (B, t);  prefix_emb: fp32 (B, m, C) or NULL;  cls: int64 (B) class ids used
+ *   when prefix_emb is NULL and m == 1 (GPTClass);  logits_out: fp32 (B, m+t, head_out);
+ *   att_out: optional fp32 (B, n_head, m+t, m+t) = last block's attention probabilities.
+ * Synchronises `stream` (reports out-of-range token / class ids as MGV_ERR_INVALID). */
+int mgv_gpt_forward(mgv_gpt_t* g, const int64_t* idx, int B, int t, const float* prefix_emb, const int64_t* cls,
+                    int m, float* logits_out, float* att_out, mgv_stream_t stream);
+
+/* Lit_minGPT.sample (:293-360) with a KV cache and a CUDA-graph decode loop.
+ *   x0: int64 (B, t0) prompt (t0 may be 0);  x_out: int64 (B, t0+steps), first t0 columns = x0;
+ *   att_out: optional fp32 (B, n_head, Tf, Tf), Tf = m + t0 + steps - 1 (the attention the
+ *   reference returns from its last forward);  do_sample 0 = greedy (torch.topk(probs,1)),
+ *   1 = multinomial;  top_k 0 = None;  seed keys the Philox stream (row b, position p).
+ * Fails with MGV_ERR_INVALID when t0 + steps - 1 + m > block_size (the reference's assert).
+ * Synchronises. */
+int mgv_gpt_generate(mgv_gpt_t* g, const int64_t* x0, int B, int t0, const float* prefix_emb, const int64_t* cls,
+                     int m, int steps, float temperature, int do_sample, int top_k, uint64_t seed,
+                     int64_t* x_out, float* att_out, int use_graph, mgv_stream_t stream);
+
+/* number of kernels libmgv launched in the last forward / generate call on this handle */
+int64_t mgv_gpt_last_launches(const mgv_gpt_t* g);
+
+/* ------------------------------------------------------------------ (3) VQVAE -------- */
+
+typedef struct mgv_vqvae mgv_vqvae_t;
+
+/* LitVQVAE(num_embeddings, embedding_dim) with the module-level architecture constants of
+ * vqvae/big_model_attn_gan.py:521-530 (ch 128, ch_mult 1,1,2,2,4, 2 res blocks, attention
+ * at the 5x53 level, z_channels 256, 80x848 mels). */
+int mgv_vqvae_create(int num_embeddings, int embedding_dim, mgv_vqvae_t** out);
+int mgv_vqvae_destroy(mgv_vqvae_t* v);
+
+/* state_dict key relative to LitVQVAE ("_decoder.up.0.block.1.conv1.weight",
+ * "post_quant_conv.bias", "_vq_vae._embedding.weight", "_encoder.conv_in.weight", ...);
+ * "discriminator.*" keys are accepted and ignored.  src: fp32 device. */
+int mgv_vqvae_load_weight(mgv_vqvae_t* v, const char* name, const float* src, int64_t numel, mgv_stream_t stream);
+
+/* Lit_minGPT.decode_to_img after code_reader (transformer/minGPT.py:515-528):
+ * get_codebook_entry + post_quant_conv + Decoder.forward (big_model_attn_gan.py:56-71,
+ * :610-614, :361-392).  idx: int64 (B, H*W) row-major code grid; mel_out: fp32 (B,1,80,848). */
+int mgv_vqvae_decode_codes(mgv_vqvae_t* v, const int64_t* idx, int B, float* mel_out, mgv_stream_t stream);
+
+/* LitVQVAE.decode(quant) (:610-614): quant fp32 (B, 256, 5, 53) BCHW -> mel (B,1,80,848). */
+int mgv_vqvae_decode(mgv_vqvae_t* v, const float* quant_bchw, int B, float* mel_out, mgv_stream_t stream);
+
+/* LitVQVAE.encode(x) (:604-608): mel fp32 (B,1,80,848) -> z fp32 (B, 256, 5, 53) BCHW. */
+int mgv_vqvae_encode(mgv_vqvae_t* v, const float* mel, int B, float* z_out, mgv_stream_t stream);
+
+int64_t mgv_vqvae_last_launches(const mgv_vqvae_t* v);
+
+/* ------------------------------------------------------------------ test hooks ------- */
+
+/* D[M,N] = A[M,K] B[N,K]^T (+bias) through the tcgen05 GEMM (impl 0) or the SIMT fp32
+ * reference kernel (impl 1).  A, B bf16; epi as GemmEpilogue in csrc/gemm_tc.cuh.
+ * Used by tests/ to cross-check the tensor-core path on device. */
+int mgv_test_gemm(int impl, const void* A, const void* B, int M, int N, int K, int epi, const float* bias,
+                  void* out, const void* resid, int bn, int split_k, mgv_stream_t stream);
+
+/* 3x3 convolution (stride 1 pad 1, or stride 2 with the reference's (0,1,0,1) padding) over
+ * NHWC bf16 input through the implicit-GEMM path (impl 0) or the SIMT reference (impl 1).
+ * w: bf16 (Cout, 3, 3, Cin). */
+int mgv_test_conv3x3(int impl, const void* x_nhwc, const void* w, const float* bias, int n_img, int Hin, int Win,
+                     int Cin, int Cout, int stride, void* out_nhwc, const void* resid_nhwc, mgv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGV_H_ */

@@ -1,0 +1,436 @@
+// tcgen05 GEMM / implicit-GEMM convolution kernel (see gemm_tc.cuh).
+//
+// CTA = 192 threads: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
+// issuer (one lane), warps 2..5 = epilogue (each owns one 32-lane TMEM quarter).
+// Tile = 128 (M) x BN (N) x 64 (K) per pipeline stage; the ring of `stages` stages is
+// filled by TMA with the 128-byte swizzle and drained by tcgen05.mma reading smem
+// descriptors; the fp32 accumulator lives in TMEM (BN columns) and is read back with
+// tcgen05.ld for the fused epilogue.
+//
+// Weight streaming (decode step): when launched with programmatic dependent launch the
+// producer issues the B (weight) loads of the first ring pass BEFORE griddepcontrol.wait,
+// so weights stream from HBM while the upstream kernel is still finishing; only the A
+// (activation) loads wait for the dependency.
+#include "gemm_tc.cuh"
+
+namespace mgv {
+
+using namespace sm100;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int GEMM_THREADS = 192;
+
+struct KParams {
+  int M, N, K;
+  int kb_per_split;  // 64-wide k blocks handled by one blockIdx.z
+  int stages;
+  int epi;
+  const float* bias;
+  void* out;
+  const void* resid;
+  long long ldo;
+  // conv
+  int a_mode;
+  int H, W, Cin, wb, hb, tiles_x, tiles_y, stride, pad;
+  float* gn_sum;
+  int gn_group_ch;
+  int evict_first_b;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int n0 = blockIdx.y * BN;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int total_kb = p.K / BK;
+  int nkb = total_kb - kb0;
+  if (nkb > p.kb_per_split) nkb = p.kb_per_split;
+
+  int m0 = 0, img = 0, x0 = 0, y0 = 0;
+  if (p.a_mode == A_PLAIN) {
+    m0 = blockIdx.x * BM;
+  } else {
+    int t = blockIdx.x;
+    int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    int ty = t % p.tiles_y;
+    img = t / p.tiles_y;
+    x0 = tx * p.wb;
+    y0 = ty * p.hb;
+  }
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      const uint64_t hint_b = p.evict_first_b ? kEvictFirst : kEvictNormal;
+      const uint64_t hint_a = kEvictNormal;
+      const int cblocks = (p.a_mode == A_PLAIN) ? 1 : (p.Cin / BK);
+      auto load_a = [&](int kb, int s) {
+        uint8_t* dst = smem + s * STAGE_BYTES;
+        if (p.a_mode == A_PLAIN) {
+          tma_load_2d(dst, &tmA, &full_bar[s], (kb0 + kb) * BK, m0, hint_a);
+        } else {
+          const int kk = kb0 + kb;
+          const int tap = kk / cblocks;
+          const int c0 = (kk - tap * cblocks) * BK;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          // input coordinate of the tile's first pixel for this tap
+          const int xi = x0 * p.stride + dx - p.pad;
+          const int yi = y0 * p.stride + dy - p.pad;
+          tma_load_4d(dst, &tmA, &full_bar[s], c0, xi, yi, img, hint_a);
+        }
+      };
+      auto load_b = [&](int kb, int s) {
+        uint8_t* dst = smem + s * STAGE_BYTES + A_STAGE_BYTES;
+        tma_load_2d(dst, &tmB, &full_bar[s], (kb0 + kb) * BK, n0, hint_b);
+      };
+      const int pre = nkb < stages ? nkb : stages;
+      for (int kb = 0; kb < pre; ++kb) {  // weights first: they do not depend on the upstream grid
+        mbar_arrive_expect_tx(&full_bar[kb], STAGE_BYTES);
+        load_b(kb, kb);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < pre; ++kb) load_a(kb, kb);
+      for (int kb = pre; kb < nkb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        load_a(kb, s);
+        load_b(kb, s);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
+          umma_bf16(tmem_base, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32),
+                    idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // =========================== epilogue ===========================
+    pdl_wait();  // residual / output buffers belong to the upstream grid
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    const int r_local = quarter * 32 + lane;
+    bool row_ok;
+    long long out_row;  // element offset of this thread's output row
+    if (p.a_mode == A_PLAIN) {
+      const int row = m0 + r_local;
+      row_ok = row < p.M;
+      out_row = static_cast<long long>(row) * p.ldo;
+    } else {
+      const int ly = r_local / p.wb, lx = r_local - ly * p.wb;
+      const int x = x0 + lx, y = y0 + ly;
+      row_ok = (x < p.W) && (y < p.H);
+      out_row = ((static_cast<long long>(img) * p.H + y) * p.W + x) * p.ldo;
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool add_bias = p.bias != nullptr && (p.epi != EPI_F32_ATOMIC || blockIdx.z == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (add_bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          v[4 * j + 0] += b.x;
+          v[4 * j + 1] += b.y;
+          v[4 * j + 2] += b.z;
+          v[4 * j + 3] += b.w;
+        }
+      }
+      if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU || p.epi == EPI_BF16_RESID) {
+        if (p.epi == EPI_BF16_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (p.epi == EPI_BF16_RESID && row_ok) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + out_row + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = __ldg(r4 + j);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(w[e]);
+              v[8 * j + 2 * e] += f.x;
+              v[8 * j + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        if (row_ok) {
+          uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_row + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (p.gn_sum != nullptr) {
+          // GroupNorm statistics of the stored (bf16-rounded) values; a tile never spans images.
+          const int gch = p.gn_group_ch;          // 4, 8 or 16 channels per group
+          const int ngroups_chunk = 32 / gch;
+          float* dst = p.gn_sum + (static_cast<long long>(img) * (p.N / gch) + col0 / gch) * 2;
+          for (int g = 0; g < ngroups_chunk; ++g) {
+            float s = 0.f, ss = 0.f;
+            if (row_ok) {
+              for (int e = 0; e < gch; e += 2) {
+                const float2 f = unpack_bf16x2(pk[(g * gch + e) >> 1]);
+                s += f.x + f.y;
+                ss += f.x * f.x + f.y * f.y;
+              }
+            }
+            s = warp_sum(s);
+            ss = warp_sum(ss);
+            if (lane == 0) {
+              atomicAdd(dst + 2 * g, s);
+              atomicAdd(dst + 2 * g + 1, ss);
+            }
+          }
+        }
+      } else if (row_ok) {
+        float* o = static_cast<float*>(p.out) + out_row + col0;
+        if (p.epi == EPI_F32_ATOMIC) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        } else {
+          if (p.epi == EPI_F32_RESID) {
+            const float4* r4 = reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + out_row + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q = r4[j];
+              v[4 * j + 0] += q.x;
+              v[4 * j + 1] += q.y;
+              v[4 * j + 2] += q.z;
+              v[4 * j + 3] += q.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+  }
+
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------- SIMT reference
+__global__ void gemm_ref_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                KParams p, long long lda, int n_img, int Hin, int Win) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(p.M) * p.N) return;
+  const int n = static_cast<int>(idx % p.N);
+  const long long m = idx / p.N;
+  float acc = 0.f;
+  if (p.a_mode == A_PLAIN) {
+    for (int k = 0; k < p.K; ++k)
+      acc = fmaf(__bfloat162float(A[m * lda + k]), __bfloat162float(B[static_cast<long long>(n) * p.K + k]), acc);
+  } else {
+    const int x = static_cast<int>(m % p.W);
+    const int y = static_cast<int>((m / p.W) % p.H);
+    const int img = static_cast<int>(m / (static_cast<long long>(p.W) * p.H));
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap % 3;
+      const int xi = x * p.stride + dx - p.pad, yi = y * p.stride + dy - p.pad;
+      if (xi < 0 || yi < 0 || xi >= Win || yi >= Hin) continue;
+      const __nv_bfloat16* a = A + ((static_cast<long long>(img) * Hin + yi) * Win + xi) * p.Cin;
+      const __nv_bfloat16* b = B + static_cast<long long>(n) * p.K + tap * p.Cin;
+      for (int c = 0; c < p.Cin; ++c) acc = fmaf(__bfloat162float(a[c]), __bfloat162float(b[c]), acc);
+    }
+  }
+  if (p.bias) acc += p.bias[n];
+  const long long o = m * p.ldo + n;
+  switch (p.epi) {
+    case EPI_BF16: static_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(acc); break;
+    case EPI_BF16_GELU: static_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(gelu_erf(acc)); break;
+    case EPI_BF16_RESID:
+      static_cast<__nv_bfloat16*>(p.out)[o] =
+          __float2bfloat16(acc + __bfloat162float(static_cast<const __nv_bfloat16*>(p.resid)[o]));
+      break;
+    case EPI_F32: static_cast<float*>(p.out)[o] = acc; break;
+    case EPI_F32_RESID: static_cast<float*>(p.out)[o] = static_cast<const float*>(p.resid)[o] + acc; break;
+    case EPI_F32_ATOMIC: static_cast<float*>(p.out)[o] += acc; break;
+  }
+}
+
+int fill_params(const GemmArgs& a, KParams& p) {
+  MGV_REQUIRE(a.A && a.B && a.out, "gemm: null operand");
+  MGV_REQUIRE(a.K > 0 && a.K % BK == 0, "gemm: K=%d must be a positive multiple of %d", a.K, BK);
+  MGV_REQUIRE(a.N > 0 && a.N % 32 == 0, "gemm: N=%d must be a multiple of 32", a.N);
+  MGV_REQUIRE(a.M > 0, "gemm: M=%d", a.M);
+  MGV_REQUIRE(a.split_k >= 1, "gemm: split_k=%d", a.split_k);
+  MGV_REQUIRE(a.split_k == 1 || a.epi == EPI_F32_ATOMIC, "gemm: split_k>1 needs EPI_F32_ATOMIC");
+  if (a.epi == EPI_F32_RESID || a.epi == EPI_BF16_RESID) MGV_REQUIRE(a.resid, "gemm: residual epilogue without resid");
+  memset(&p, 0, sizeof(p));
+  p.M = a.M;
+  p.N = a.N;
+  p.K = a.K;
+  p.epi = a.epi;
+  p.bias = a.bias;
+  p.out = a.out;
+  p.resid = a.resid;
+  p.ldo = a.ldo ? a.ldo : a.N;
+  p.a_mode = a.a_mode;
+  p.evict_first_b = a.weights_evict_first ? 1 : 0;
+  p.gn_sum = a.gn_sum;
+  p.gn_group_ch = a.gn_group_ch;
+  if (a.gn_sum) {
+    MGV_REQUIRE(a.a_mode == A_CONV3x3 || a.n_img > 0, "gemm: gn_sum needs image geometry");
+    MGV_REQUIRE(a.gn_group_ch == 4 || a.gn_group_ch == 8 || a.gn_group_ch == 16, "gemm: gn_group_ch=%d", a.gn_group_ch);
+    MGV_REQUIRE(a.epi == EPI_BF16 || a.epi == EPI_BF16_RESID, "gemm: gn_sum needs a bf16 epilogue");
+  }
+  if (a.a_mode == A_CONV3x3) {
+    MGV_REQUIRE(a.n_img > 0 && a.H > 0 && a.W > 0 && a.Cin > 0 && a.Cin % BK == 0, "conv: bad geometry");
+    MGV_REQUIRE(a.K == 9 * a.Cin, "conv: K=%d != 9*Cin", a.K);
+    MGV_REQUIRE(a.M == a.n_img * a.H * a.W, "conv: M mismatch");
+    MGV_REQUIRE(a.stride == 1 || a.stride == 2, "conv: stride");
+    p.H = a.H;
+    p.W = a.W;
+    p.Cin = a.Cin;
+    p.stride = a.stride;
+    p.pad = a.pad;
+    int wb = 16;
+    while (wb < 128 && wb < a.W) wb *= 2;
+    p.wb = wb;
+    p.hb = BM / wb;
+    p.tiles_x = ceil_div(a.W, p.wb);
+    p.tiles_y = ceil_div(a.H, p.hb);
+  }
+  return MGV_OK;
+}
+
+template <int BN>
+int launch_tc(const GemmArgs& a, KParams& p) {
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  const int total_kb = a.K / BK;
+  p.kb_per_split = ceil_div(total_kb, a.split_k);
+  const int splits = ceil_div(total_kb, p.kb_per_split);
+  int max_stages = (200 * 1024) / STAGE_BYTES;
+  if (a.max_stages > 0 && a.max_stages < max_stages) max_stages = a.max_stages;
+  p.stages = p.kb_per_split < max_stages ? p.kb_per_split : max_stages;
+  if (p.stages < 1) p.stages = 1;
+  const size_t smem = static_cast<size_t>(p.stages) * STAGE_BYTES + (2 * p.stages + 1) * 8 + 16 + 1024;
+
+  CUtensorMap tmA, tmB;
+  if (a.a_mode == A_PLAIN) {
+    const int64_t lda = a.lda ? a.lda : a.K;
+    MGV_TRY(make_tmap_2d_bf16(&tmA, a.A, a.K, a.M, lda * 2, BK, BM));
+  } else {
+    MGV_TRY(make_tmap_nhwc_bf16(&tmA, a.A, a.Cin, a.Win, a.Hin, a.n_img, BK, p.wb, p.hb, a.stride));
+  }
+  MGV_TRY(make_tmap_2d_bf16(&tmB, a.B, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, BN));
+
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid;
+  if (a.a_mode == A_PLAIN)
+    grid = dim3(ceil_div(a.M, BM), ceil_div(a.N, BN), splits);
+  else
+    grid = dim3(p.tiles_x * p.tiles_y * a.n_img, ceil_div(a.N, BN), 1);
+  LaunchCfg lc(grid, dim3(GEMM_THREADS), smem, a.stream, a.pdl);
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN>, tmA, tmB, p));
+  return MGV_OK;
+}
+
+}  // namespace
+
+int gemm_bf16_tc(const GemmArgs& a) {
+  KParams p;
+  MGV_TRY(fill_params(a, p));
+  if (a.a_mode == A_CONV3x3) MGV_REQUIRE(a.split_k == 1, "conv: split_k unsupported");
+  switch (a.bn) {
+    case 32: return launch_tc<32>(a, p);
+    case 64: return launch_tc<64>(a, p);
+    case 128: return launch_tc<128>(a, p);
+    case 256: return launch_tc<256>(a, p);
+    default: set_error("gemm: bn=%d not in {32,64,128,256}", a.bn); return MGV_ERR_INVALID;
+  }
+}
+
+int gemm_bf16_ref(const GemmArgs& a) {
+  KParams p;
+  MGV_TRY(fill_params(a, p));
+  const long long total = static_cast<long long>(a.M) * a.N;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  gemm_ref_kernel<<<static_cast<unsigned>(blocks), threads, 0, a.stream>>>(
+      static_cast<const __nv_bfloat16*>(a.A), static_cast<const __nv_bfloat16*>(a.B), p, a.lda ? a.lda : a.K, a.n_img,
+      a.Hin, a.Win);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+}  // namespace mgv

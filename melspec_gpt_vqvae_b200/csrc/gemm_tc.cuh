@@ -1,0 +1,62 @@
+// tcgen05 / TMEM / TMA GEMM used by every dense contraction on the token path:
+//   * minGPT Linear layers (prefill and the per-token decode step, where it is a
+//     weight-streaming kernel: M = batch, split-K over the grid),
+//   * the VQVAE 1x1 convolutions (plain GEMM over NHWC pixels),
+//   * the VQVAE 3x3 convolutions as implicit GEMM: the A operand is fetched by TMA from
+//     the NHWC activation tensor with one shifted 4-D box per filter tap (zero fill at
+//     the image border = the convolution's zero padding; element stride 2 = stride-2 conv).
+// D[M,N] = A[M,K] * B[N,K]^T, A/B bf16 K-major, fp32 accumulation in TMEM.
+#pragma once
+#include "mgv_sm100.cuh"
+
+namespace mgv {
+
+enum GemmEpilogue : int {
+  EPI_BF16 = 0,        // out_bf16 = acc + bias
+  EPI_BF16_GELU = 1,   // out_bf16 = gelu_erf(acc + bias)
+  EPI_F32 = 2,         // out_f32 = acc + bias
+  EPI_F32_RESID = 3,   // out_f32 = resid_f32 + acc + bias        (resid may alias out)
+  EPI_F32_ATOMIC = 4,  // out_f32 += acc (+ bias from split 0)     (split-K; out pre-initialised)
+  EPI_BF16_RESID = 5,  // out_bf16 = resid_bf16 + acc + bias       (conv residual blocks)
+};
+
+enum GemmAMode : int {
+  A_PLAIN = 0,    // A is a row-major [M,K] matrix
+  A_CONV3x3 = 1,  // A rows are output pixels of a 3x3 convolution over NHWC input
+};
+
+struct GemmArgs {
+  // operands
+  const void* A = nullptr;  // bf16: [M,K] (lda elements) or NHWC input [N,Hin,Win,Cin]
+  const void* B = nullptr;  // bf16 weights [N,K] row-major (K = 9*Cin for conv, tap-major)
+  int M = 0, N = 0, K = 0;
+  int64_t lda = 0;          // elements; 0 -> K
+  // epilogue
+  int epi = EPI_BF16;
+  const float* bias = nullptr;  // [N] or null
+  void* out = nullptr;
+  const void* resid = nullptr;
+  int64_t ldo = 0;  // elements; 0 -> N
+  // tiling
+  int bn = 128;     // 32 / 64 / 128 / 256
+  int split_k = 1;  // EPI_F32_ATOMIC only when > 1
+  int max_stages = 0;
+  // conv geometry (A_CONV3x3): output HxW, input Hin x Win, stride 1 or 2
+  int a_mode = A_PLAIN;
+  int n_img = 0, H = 0, W = 0, Hin = 0, Win = 0, Cin = 0, stride = 1, pad = 1;
+  // GroupNorm statistics fused into the epilogue (conv): per (image, channel-group of
+  // `gn_group_ch` output channels) sum and sum of squares of the bf16-rounded outputs.
+  float* gn_sum = nullptr;  // [n_img, N / gn_group_ch, 2] fp32, pre-zeroed
+  int gn_group_ch = 0;
+  // launch
+  bool pdl = false;
+  bool weights_evict_first = false;
+  cudaStream_t stream = nullptr;
+};
+
+int gemm_bf16_tc(const GemmArgs& a);
+
+// SIMT fp32 reference of the same contract (tests / on-device cross-checks only).
+int gemm_bf16_ref(const GemmArgs& a);
+
+}  // namespace mgv

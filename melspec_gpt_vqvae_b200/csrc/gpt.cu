@@ -1,0 +1,547 @@
+// minGPT handle: packed bf16 weights, KV cache, prefill (teacher-forced forward) and the
+// CUDA-graph decode loop.  reference: transformer/minGPT.py:121-212 (GPT, GPTClass),
+// :293-360 (Lit_minGPT.sample).
+#include <string>
+#include <vector>
+#include <stdlib.h>
+#include "gemm_tc.cuh"
+#include "gpt_kernels.cuh"
+#include "gpt.cuh"
+
+namespace mgv {
+
+namespace {
+
+__global__ void cvt_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+
+int cvt_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s) {
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  if (blocks < 1) blocks = 1;
+  cvt_f32_bf16_kernel<<<blocks, 256, 0, s>>>(in, out, n);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int pick_bn(int N) {
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 32;
+}
+
+}  // namespace
+
+struct GptLayer {
+  float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  __nv_bfloat16 *wqkv, *wproj, *wfc1, *wfc2;
+  float *bqkv, *bproj, *bfc1, *bfc2;
+};
+
+struct DecodeTiles {
+  int qkv_bn = 128, qkv_split = 8;
+  int proj_bn = 64, proj_split = 8;
+  int fc1_bn = 128, fc1_split = 4;
+  int fc2_bn = 64, fc2_split = 8;
+};
+
+struct Gpt {
+  GptConfig cfg;
+  int C, L, nh, V, Vout, Tmax;
+  // parameters
+  void* slab = nullptr;
+  size_t slab_bytes = 0;
+  float *tok_emb, *pos_emb, *embedder, *lnf_w, *lnf_b;
+  __nv_bfloat16* whead;
+  std::vector<GptLayer> layers;
+  std::vector<unsigned char> loaded;  // per tensor
+  int n_tensors = 0;
+  // workspaces
+  int ws_rows = 0;  // prefill rows capacity
+  float* x = nullptr;
+  __nv_bfloat16 *ln = nullptr, *qkv = nullptr, *y = nullptr, *h = nullptr;
+  int dec_B = 0;  // decode batch capacity
+  float *dx = nullptr, *dqkv32 = nullptr, *dh32 = nullptr;
+  __nv_bfloat16 *dln = nullptr, *dy = nullptr, *dh = nullptr, *kv = nullptr;
+  int* d_state = nullptr;  // [0]=pos, [1]=done counter, [2]=err flag
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  bool pdl = false;
+  DecodeTiles tiles;
+  long long launches = 0;  // kernels launched by the last forward / generate call
+
+  __nv_bfloat16* kcache(int l) const {
+    return kv + (static_cast<size_t>(l) * 2) * dec_B * nh * Tmax * GPT_HEAD_DIM;
+  }
+  __nv_bfloat16* vcache(int l) const {
+    return kv + (static_cast<size_t>(l) * 2 + 1) * dec_B * nh * Tmax * GPT_HEAD_DIM;
+  }
+};
+
+namespace {
+
+size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align256(n * sizeof(T));
+    return p;
+  }
+};
+
+void carve_params(Gpt* g, char* base, size_t* total) {
+  Carver c{base};
+  const size_t C = g->C;
+  g->tok_emb = c.take<float>(static_cast<size_t>(g->V) * C);
+  g->pos_emb = c.take<float>(static_cast<size_t>(g->cfg.block_size) * C);
+  g->embedder = c.take<float>(static_cast<size_t>(g->cfg.class_size > 0 ? g->cfg.class_size : 1) * C);
+  g->lnf_w = c.take<float>(C);
+  g->lnf_b = c.take<float>(C);
+  g->whead = c.take<__nv_bfloat16>(static_cast<size_t>(g->Vout) * C);
+  g->layers.resize(g->L);
+  for (int l = 0; l < g->L; ++l) {
+    GptLayer& y = g->layers[l];
+    y.ln1_w = c.take<float>(C);
+    y.ln1_b = c.take<float>(C);
+    y.ln2_w = c.take<float>(C);
+    y.ln2_b = c.take<float>(C);
+    y.wqkv = c.take<__nv_bfloat16>(3 * C * C);
+    y.bqkv = c.take<float>(3 * C);
+    y.wproj = c.take<__nv_bfloat16>(C * C);
+    y.bproj = c.take<float>(C);
+    y.wfc1 = c.take<__nv_bfloat16>(4 * C * C);
+    y.bfc1 = c.take<float>(4 * C);
+    y.wfc2 = c.take<__nv_bfloat16>(4 * C * C);
+    y.bfc2 = c.take<float>(C);
+  }
+  *total = c.off;
+}
+
+int ensure_prefill_ws(Gpt* g, int rows) {
+  if (rows <= g->ws_rows) return MGV_OK;
+  cudaFree(g->x); cudaFree(g->ln); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->h);
+  g->x = nullptr; g->ln = g->qkv = g->y = g->h = nullptr;
+  g->ws_rows = 0;
+  const size_t C = g->C, R = rows;
+  MGV_CHECK_CUDA(cudaMalloc(&g->x, R * C * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&g->ln, R * C * 2));
+  MGV_CHECK_CUDA(cudaMalloc(&g->qkv, R * 3 * C * 2));
+  MGV_CHECK_CUDA(cudaMalloc(&g->y, R * C * 2));
+  MGV_CHECK_CUDA(cudaMalloc(&g->h, R * 4 * C * 2));
+  g->ws_rows = rows;
+  return MGV_OK;
+}
+
+int ensure_decode_ws(Gpt* g, int B) {
+  if (B <= g->dec_B) return MGV_OK;
+  cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
+  cudaFree(g->kv);
+  g->dx = g->dqkv32 = g->dh32 = nullptr;
+  g->dln = g->dy = g->dh = g->kv = nullptr;
+  g->dec_B = 0;
+  const size_t C = g->C, R = B;
+  MGV_CHECK_CUDA(cudaMalloc(&g->dx, R * C * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&g->dqkv32, R * 3 * C * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&g->dh32, R * 4 * C * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&g->dln, R * C * 2));
+  MGV_CHECK_CUDA(cudaMalloc(&g->dy, R * C * 2));
+  MGV_CHECK_CUDA(cudaMalloc(&g->dh, R * 4 * C * 2));
+  const size_t kv_elems = static_cast<size_t>(g->L) * 2 * R * g->nh * g->Tmax * GPT_HEAD_DIM;
+  MGV_CHECK_CUDA(cudaMalloc(&g->kv, kv_elems * 2));
+  g->dec_B = B;
+  return MGV_OK;
+}
+
+int check_loaded(const Gpt* g) {
+  for (int i = 0; i < g->n_tensors; ++i)
+    if (!g->loaded[i]) {
+      // the class embedder is optional (plain GPT has none)
+      if (i == 2) continue;
+      set_error("gpt: weight tensor #%d was never loaded (call mgv_gpt_load_weight for every state_dict key)", i);
+      return MGV_ERR_STATE;
+    }
+  return MGV_OK;
+}
+
+// layers of the prefill / teacher-forced pass over `rows` = B*T residual rows already in g->x
+int run_layers_prefill(Gpt* g, int B, int T, float* att_out, int att_T, bool write_cache, cudaStream_t s) {
+  const int C = g->C, rows = B * T;
+  for (int l = 0; l < g->L; ++l) {
+    const GptLayer& w = g->layers[l];
+    MGV_TRY(gpt_layernorm(g->x, w.ln1_w, w.ln1_b, rows, C, g->ln, nullptr, 0, s, false));
+    GemmArgs a;
+    a.stream = s;
+    a.A = g->ln; a.B = w.wqkv; a.M = rows; a.N = 3 * C; a.K = C;
+    a.epi = EPI_BF16; a.bias = w.bqkv; a.out = g->qkv; a.bn = pick_bn(a.N);
+    MGV_TRY(gemm_bf16_tc(a));
+    float* att = (l == g->L - 1) ? att_out : nullptr;
+    MGV_TRY(gpt_attention_prefill(g->qkv, B, T, g->nh, g->cfg.n_unmasked, g->y, att, att_T,
+                                  write_cache ? g->kcache(l) : nullptr, write_cache ? g->vcache(l) : nullptr, g->Tmax,
+                                  s));
+    a = GemmArgs();
+    a.stream = s;
+    a.A = g->y; a.B = w.wproj; a.M = rows; a.N = C; a.K = C;
+    a.epi = EPI_F32_RESID; a.bias = w.bproj; a.out = g->x; a.resid = g->x; a.bn = pick_bn(a.N);
+    MGV_TRY(gemm_bf16_tc(a));
+    MGV_TRY(gpt_layernorm(g->x, w.ln2_w, w.ln2_b, rows, C, g->ln, nullptr, 0, s, false));
+    a = GemmArgs();
+    a.stream = s;
+    a.A = g->ln; a.B = w.wfc1; a.M = rows; a.N = 4 * C; a.K = C;
+    a.epi = EPI_BF16_GELU; a.bias = w.bfc1; a.out = g->h; a.bn = pick_bn(a.N);
+    MGV_TRY(gemm_bf16_tc(a));
+    a = GemmArgs();
+    a.stream = s;
+    a.A = g->h; a.B = w.wfc2; a.M = rows; a.N = C; a.K = 4 * C;
+    a.epi = EPI_F32_RESID; a.bias = w.bfc2; a.out = g->x; a.resid = g->x; a.bn = pick_bn(a.N);
+    MGV_TRY(gemm_bf16_tc(a));
+    g->launches += 7;
+  }
+  return MGV_OK;
+}
+
+int read_err_flag(Gpt* g, cudaStream_t s, const char* what) {
+  int flag = 0;
+  MGV_CHECK_CUDA(cudaMemcpyAsync(&flag, g->d_state + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+  MGV_CHECK_CUDA(cudaStreamSynchronize(s));
+  if (flag != 0) {
+    MGV_CHECK_CUDA(cudaMemsetAsync(g->d_state + 2, 0, sizeof(int), s));
+    set_error("%s: %s index out of range", what, flag == 1 ? "class" : "token");
+    return MGV_ERR_INVALID;
+  }
+  return MGV_OK;
+}
+
+}  // namespace
+
+int gpt_create(const GptConfig* cfg, Gpt** out) {
+  MGV_REQUIRE(cfg && out, "gpt_create: null");
+  MGV_TRY(check_device());
+  MGV_REQUIRE(cfg->n_embd % cfg->n_head == 0 && cfg->n_embd / cfg->n_head == GPT_HEAD_DIM,
+              "gpt: head dim %d unsupported (need %d)", cfg->n_head ? cfg->n_embd / cfg->n_head : 0, GPT_HEAD_DIM);
+  MGV_REQUIRE(cfg->n_embd % 64 == 0 && cfg->n_embd <= 2048, "gpt: n_embd=%d unsupported", cfg->n_embd);
+  MGV_REQUIRE(cfg->block_size >= 1 && cfg->block_size <= GPT_MAX_T, "gpt: block_size=%d unsupported (<= %d)",
+              cfg->block_size, GPT_MAX_T);
+  MGV_REQUIRE(cfg->vocab_size >= 1 && cfg->n_layer >= 1, "gpt: bad config");
+  const int vout = cfg->head_out > 0 ? cfg->head_out : cfg->vocab_size;
+  MGV_REQUIRE(vout % 32 == 0, "gpt: head output size %d must be a multiple of 32", vout);
+  Gpt* g = new Gpt();
+  g->cfg = *cfg;
+  g->C = cfg->n_embd;
+  g->L = cfg->n_layer;
+  g->nh = cfg->n_head;
+  g->V = cfg->vocab_size;
+  g->Vout = vout;
+  g->Tmax = cfg->block_size;
+  size_t total = 0;
+  carve_params(g, nullptr, &total);
+  g->slab_bytes = total;
+  if (cudaMalloc(&g->slab, total) != cudaSuccess) {
+    set_error("gpt_create: cudaMalloc(%zu) failed", total);
+    delete g;
+    return MGV_ERR_CUDA;
+  }
+  carve_params(g, static_cast<char*>(g->slab), &total);
+  g->n_tensors = 6 + 12 * g->L;
+  g->loaded.assign(g->n_tensors, 0);
+  cudaMalloc(&g->d_state, 4 * sizeof(int));
+  cudaMemset(g->d_state, 0, 4 * sizeof(int));
+  cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&g->ev_in, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&g->ev_out, cudaEventDisableTiming);
+  const char* e = getenv("MGV_PDL");
+  g->pdl = e && atoi(e) != 0;
+  const char* tl = getenv("MGV_DECODE_TILES");
+  if (tl) {
+    DecodeTiles t;
+    if (sscanf(tl, "%d,%d,%d,%d,%d,%d,%d,%d", &t.qkv_bn, &t.qkv_split, &t.proj_bn, &t.proj_split, &t.fc1_bn,
+               &t.fc1_split, &t.fc2_bn, &t.fc2_split) == 8)
+      g->tiles = t;
+  }
+  if (cudaGetLastError() != cudaSuccess) {
+    set_error("gpt_create: CUDA resource creation failed");
+    delete g;
+    return MGV_ERR_CUDA;
+  }
+  *out = g;
+  return MGV_OK;
+}
+
+int gpt_destroy(Gpt* g) {
+  if (!g) return MGV_OK;
+  cudaFree(g->slab);
+  cudaFree(g->x); cudaFree(g->ln); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->h);
+  cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
+  cudaFree(g->kv);
+  cudaFree(g->d_state);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  if (g->ev_in) cudaEventDestroy(g->ev_in);
+  if (g->ev_out) cudaEventDestroy(g->ev_out);
+  delete g;
+  return MGV_OK;
+}
+
+// name = reference state_dict key (transformer/minGPT.py: GPT.__init__ :135-149, Block :97-105,
+// CausalSelfAttention :56-63, GPTClass :207).  src = fp32 device pointer.
+int gpt_load_weight(Gpt* g, const char* name, const float* src, long long numel, cudaStream_t s) {
+  MGV_REQUIRE(g && name && src, "gpt_load_weight: null");
+  const size_t C = g->C;
+  auto copy_f32 = [&](float* dst, size_t n, int slot) -> int {
+    MGV_REQUIRE(static_cast<size_t>(numel) == n, "gpt_load_weight(%s): numel %lld != expected %zu", name, numel, n);
+    MGV_CHECK_CUDA(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, s));
+    g->loaded[slot] = 1;
+    return MGV_OK;
+  };
+  auto copy_bf16 = [&](__nv_bfloat16* dst, size_t n, int slot, unsigned char bit) -> int {
+    MGV_REQUIRE(static_cast<size_t>(numel) == n, "gpt_load_weight(%s): numel %lld != expected %zu", name, numel, n);
+    MGV_TRY(cvt_bf16(src, dst, static_cast<long long>(n), s));
+    g->loaded[slot] |= bit;
+    return MGV_OK;
+  };
+  std::string k(name);
+  if (k == "tok_emb.weight") return copy_f32(g->tok_emb, static_cast<size_t>(g->V) * C, 0);
+  if (k == "pos_emb") return copy_f32(g->pos_emb, static_cast<size_t>(g->cfg.block_size) * C, 1);
+  if (k == "embedder.weight") return copy_f32(g->embedder, static_cast<size_t>(g->cfg.class_size) * C, 2);
+  if (k == "ln_f.weight") return copy_f32(g->lnf_w, C, 3);
+  if (k == "ln_f.bias") return copy_f32(g->lnf_b, C, 4);
+  if (k == "head.weight") return copy_bf16(g->whead, static_cast<size_t>(g->Vout) * C, 5, 1);
+  int l = -1, consumed = 0;
+  if (sscanf(name, "blocks.%d.%n", &l, &consumed) == 1 && consumed > 0 && l >= 0 && l < g->L) {
+    GptLayer& y = g->layers[l];
+    const std::string r(name + consumed);
+    const int base = 6 + 12 * l;
+    if (r == "attn.mask") return MGV_OK;  // derived from n_unmasked; not a parameter
+    if (r == "ln1.weight") return copy_f32(y.ln1_w, C, base + 0);
+    if (r == "ln1.bias") return copy_f32(y.ln1_b, C, base + 1);
+    if (r == "ln2.weight") return copy_f32(y.ln2_w, C, base + 2);
+    if (r == "ln2.bias") return copy_f32(y.ln2_b, C, base + 3);
+    // fused QKV: rows [query | key | value]
+    if (r == "attn.query.weight") return copy_bf16(y.wqkv, C * C, base + 4, 1);
+    if (r == "attn.key.weight") return copy_bf16(y.wqkv + C * C, C * C, base + 4, 2);
+    if (r == "attn.value.weight") return copy_bf16(y.wqkv + 2 * C * C, C * C, base + 4, 4);
+    if (r == "attn.query.bias" || r == "attn.key.bias" || r == "attn.value.bias") {
+      MGV_REQUIRE(static_cast<size_t>(numel) == C, "gpt_load_weight(%s): numel", name);
+      const int part = r[5] == 'q' ? 0 : (r[5] == 'k' ? 1 : 2);
+      MGV_CHECK_CUDA(cudaMemcpyAsync(y.bqkv + part * C, src, C * 4, cudaMemcpyDeviceToDevice, s));
+      g->loaded[base + 5] |= static_cast<unsigned char>(1 << part);
+      return MGV_OK;
+    }
+    if (r == "attn.proj.weight") return copy_bf16(y.wproj, C * C, base + 6, 1);
+    if (r == "attn.proj.bias") return copy_f32(y.bproj, C, base + 7);
+    if (r == "mlp.0.weight") return copy_bf16(y.wfc1, 4 * C * C, base + 8, 1);
+    if (r == "mlp.0.bias") return copy_f32(y.bfc1, 4 * C, base + 9);
+    if (r == "mlp.2.weight") return copy_bf16(y.wfc2, 4 * C * C, base + 10, 1);
+    if (r == "mlp.2.bias") return copy_f32(y.bfc2, C, base + 11);
+  }
+  set_error("gpt_load_weight: unknown tensor name '%s'", name);
+  return MGV_ERR_INVALID;
+}
+
+namespace {
+int check_qkv_complete(const Gpt* g) {
+  for (int l = 0; l < g->L; ++l) {
+    const int base = 6 + 12 * l;
+    if (g->loaded[base + 4] != 7 || g->loaded[base + 5] != 7) {
+      set_error("gpt: layer %d query/key/value weights incomplete", l);
+      return MGV_ERR_STATE;
+    }
+  }
+  return MGV_OK;
+}
+}  // namespace
+
+// GPT.forward (minGPT.py:168-199) / GPTClass.forward (:209-212): logits [B, m+t, Vout] fp32,
+// att (optional) [B, nh, m+t, m+t] fp32 = last layer's post-softmax attention.
+int gpt_forward(Gpt* g, const long long* idx, int B, int t, const float* prefix_emb, const long long* cls, int m,
+                float* logits_out, float* att_out, cudaStream_t s) {
+  MGV_REQUIRE(g && logits_out, "gpt_forward: null");
+  MGV_TRY(check_loaded(g));
+  MGV_TRY(check_qkv_complete(g));
+  const int T = m + t;
+  MGV_REQUIRE(B >= 0 && t >= 0 && m >= 0, "gpt_forward: negative sizes");
+  MGV_REQUIRE(T >= 1, "gpt_forward: empty sequence");
+  // "Cannot forward, model block size is exhausted." (minGPT.py:178)
+  MGV_REQUIRE(T <= g->cfg.block_size, "Cannot forward, model block size is exhausted. (t=%d > block_size=%d)", T,
+              g->cfg.block_size);
+  MGV_REQUIRE(m == 0 || prefix_emb || (cls && g->loaded[2]), "gpt_forward: prefix without embeddings / embedder");
+  if (B == 0) return MGV_OK;
+  g->launches = 0;
+  const int rows = B * T;
+  MGV_TRY(ensure_prefill_ws(g, rows));
+  MGV_TRY(gpt_embed(idx, B, T, 0, t, prefix_emb, cls, g->embedder, m, g->tok_emb, g->pos_emb, g->C, g->V,
+                    g->cfg.class_size, g->x, g->d_state + 2, s, false));
+  if (att_out) MGV_CHECK_CUDA(cudaMemsetAsync(att_out, 0, static_cast<size_t>(B) * g->nh * T * T * 4, s));
+  MGV_TRY(run_layers_prefill(g, B, T, att_out, T, false, s));
+  MGV_TRY(gpt_layernorm(g->x, g->lnf_w, g->lnf_b, rows, g->C, g->ln, nullptr, 0, s, false));
+  GemmArgs a;
+  a.stream = s;
+  a.A = g->ln; a.B = g->whead; a.M = rows; a.N = g->Vout; a.K = g->C;
+  a.epi = EPI_F32; a.bias = nullptr; a.out = logits_out; a.bn = pick_bn(a.N);
+  MGV_TRY(gemm_bf16_tc(a));
+  g->launches += 3;
+  return read_err_flag(g, s, "gpt_forward");
+}
+
+namespace {
+
+int decode_gemm(Gpt* g, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, int B, int N, int K, int bn,
+                int split, int epi_direct, void* out, const void* resid, cudaStream_t s) {
+  GemmArgs a;
+  a.stream = s;
+  a.pdl = g->pdl;
+  a.weights_evict_first = true;
+  a.A = A; a.B = W; a.M = B; a.N = N; a.K = K;
+  a.bias = bias;
+  a.out = out;
+  a.bn = bn;
+  if (split > 1) {
+    a.epi = EPI_F32_ATOMIC;
+    a.split_k = split;
+  } else {
+    a.epi = epi_direct;
+    a.resid = resid;
+  }
+  g->launches += 1;
+  return gemm_bf16_tc(a);
+}
+
+// one decode position for all B sequences (enqueued on s; position read from g->d_state[0])
+int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int att_T, cudaStream_t s) {
+  const int C = g->C;
+  const DecodeTiles& tl = g->tiles;
+  for (int l = 0; l < g->L; ++l) {
+    const GptLayer& w = g->layers[l];
+    const bool qs = tl.qkv_split > 1, fs = tl.fc1_split > 1;
+    MGV_TRY(gpt_layernorm(g->dx, w.ln1_w, w.ln1_b, B, C, g->dln, qs ? g->dqkv32 : nullptr,
+                          qs ? static_cast<long long>(B) * 3 * C : 0, s, g->pdl));
+    MGV_TRY(decode_gemm(g, g->dln, w.wqkv, w.bqkv, B, 3 * C, C, tl.qkv_bn, tl.qkv_split, EPI_F32, g->dqkv32, nullptr, s));
+    MGV_TRY(gpt_attention_decode(g->dqkv32, B, g->nh, g->d_state, g->kcache(l), g->vcache(l), g->Tmax, g->dy,
+                                 (l == g->L - 1) ? att_out : nullptr, att_T, s, g->pdl));
+    MGV_TRY(decode_gemm(g, g->dy, w.wproj, w.bproj, B, C, C, tl.proj_bn, tl.proj_split, EPI_F32_RESID, g->dx, g->dx, s));
+    MGV_TRY(gpt_layernorm(g->dx, w.ln2_w, w.ln2_b, B, C, g->dln, fs ? g->dh32 : nullptr,
+                          fs ? static_cast<long long>(B) * 4 * C : 0, s, g->pdl));
+    if (fs) {
+      MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_bn, tl.fc1_split, EPI_F32, g->dh32, nullptr, s));
+      MGV_TRY(gpt_gelu_bf16(g->dh32, static_cast<long long>(B) * 4 * C, g->dh, s, g->pdl));
+      g->launches += 1;
+    } else {
+      MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_bn, 1, EPI_BF16_GELU, g->dh, nullptr, s));
+    }
+    MGV_TRY(decode_gemm(g, g->dh, w.wfc2, w.bfc2, B, C, 4 * C, tl.fc2_bn, tl.fc2_split, EPI_F32_RESID, g->dx, g->dx, s));
+    g->launches += 3;
+  }
+  MGV_TRY(gpt_sample_step(sa, s, g->pdl));
+  g->launches += 1;
+  return MGV_OK;
+}
+
+}  // namespace
+
+// Lit_minGPT.sample (minGPT.py:293-360) with a KV cache: x_out [B, t0+steps] int64 (first t0
+// columns = x0), att_out (optional) [B, nh, Tf, Tf] fp32 with Tf = m + t0 + steps - 1 = the
+// sequence length of the reference's last forward call.
+int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix_emb, const long long* cls, int m,
+                 int steps, float temperature, int do_sample, int top_k, unsigned long long seed, long long* x_out,
+                 float* att_out, int use_graph, cudaStream_t caller) {
+  MGV_REQUIRE(g && x_out, "gpt_generate: null");
+  MGV_TRY(check_loaded(g));
+  MGV_TRY(check_qkv_complete(g));
+  MGV_REQUIRE(B >= 0 && t0 >= 0 && steps >= 0, "gpt_generate: negative sizes");
+  MGV_REQUIRE(m >= 1, "gpt_generate: needs a conditioning prefix (class token or embedding)");
+  MGV_REQUIRE(prefix_emb || (cls && g->loaded[2]), "gpt_generate: prefix without embeddings / embedder");
+  MGV_REQUIRE(g->Vout == g->V, "gpt_generate: head output %d != vocab %d", g->Vout, g->V);
+  MGV_REQUIRE(top_k >= 0 && top_k <= g->V, "gpt_generate: top_k=%d out of range for vocab %d", top_k, g->V);
+  // assert x.size(1) + cond_size <= block_size at every step (minGPT.py:336)
+  MGV_REQUIRE(steps == 0 || t0 + steps - 1 + m <= g->cfg.block_size,
+              "sample: context %d + cond %d exceeds block_size %d", t0 + steps - 1, m, g->cfg.block_size);
+  if (B == 0) return MGV_OK;
+  g->launches = 0;
+  cudaStream_t s = g->stream;
+  MGV_CHECK_CUDA(cudaEventRecord(g->ev_in, caller));
+  MGV_CHECK_CUDA(cudaStreamWaitEvent(s, g->ev_in, 0));
+  MGV_TRY(ensure_decode_ws(g, B));
+  const int ld = t0 + steps;
+  if (t0 > 0)
+    MGV_CHECK_CUDA(cudaMemcpy2DAsync(x_out, static_cast<size_t>(ld) * 8, x0, static_cast<size_t>(t0) * 8,
+                                     static_cast<size_t>(t0) * 8, B, cudaMemcpyDeviceToDevice, s));
+  if (steps == 0) {
+    MGV_CHECK_CUDA(cudaEventRecord(g->ev_out, s));
+    MGV_CHECK_CUDA(cudaStreamWaitEvent(caller, g->ev_out, 0));
+    return MGV_OK;
+  }
+  const int T0 = m + t0;              // rows known before sampling starts
+  const int Tf = T0 + steps - 1;      // rows of the reference's final forward
+  if (att_out) MGV_CHECK_CUDA(cudaMemsetAsync(att_out, 0, static_cast<size_t>(B) * g->nh * Tf * Tf * 4, s));
+  // (the KV cache is laid out with dec_B as the batch extent; a smaller B uses a prefix of it)
+  // ---- prefill rows [0, T0-1): fills the KV cache only
+  if (T0 - 1 > 0) {
+    const int Tp = T0 - 1;
+    MGV_TRY(ensure_prefill_ws(g, B * Tp));
+    MGV_TRY(gpt_embed(x0, B, Tp, 0, t0, prefix_emb, cls, g->embedder, m, g->tok_emb, g->pos_emb, g->C, g->V,
+                      g->cfg.class_size, g->x, g->d_state + 2, s, false));
+    MGV_TRY(run_layers_prefill(g, B, Tp, att_out, Tf, true, s));
+    g->launches += 1;
+  }
+  // ---- embedding of row T0-1 -> decode residual stream; pos = T0-1
+  MGV_TRY(gpt_embed(x0, B, 1, T0 - 1, t0, prefix_emb, cls, g->embedder, m, g->tok_emb, g->pos_emb, g->C, g->V,
+                    g->cfg.class_size, g->dx, g->d_state + 2, s, false));
+  g->launches += 1;
+  const int init_state[2] = {T0 - 1, 0};
+  MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state, init_state, 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+
+  SampleArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.x = g->dx; sa.lnf_w = g->lnf_w; sa.lnf_b = g->lnf_b; sa.whead = g->whead;
+  sa.B = B; sa.C = g->C; sa.V = g->V;
+  sa.temperature = temperature; sa.top_k = top_k; sa.do_sample = do_sample; sa.seed = seed;
+  sa.pos_ptr = g->d_state;
+  sa.tokens = x_out; sa.tokens_ld = ld; sa.m = m;
+  sa.tok_emb = g->tok_emb; sa.pos_emb = g->pos_emb; sa.block_size = g->cfg.block_size;
+  sa.x_next = g->dx; sa.logits_out = nullptr;
+  sa.done_counter = reinterpret_cast<unsigned int*>(g->d_state + 1);
+
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  if (use_graph) {
+    MGV_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const long long before = g->launches;
+    int rc = enqueue_decode_step(g, B, sa, att_out, Tf, s);
+    const long long per_step = g->launches - before;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc != MGV_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    MGV_CHECK_CUDA(ce);
+    MGV_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    for (int k = 0; k < steps; ++k) {
+      cudaError_t le = cudaGraphLaunch(exec, s);
+      if (le != cudaSuccess) {
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        MGV_CHECK_CUDA(le);
+      }
+    }
+    g->launches = before + per_step * steps;
+  } else {
+    for (int k = 0; k < steps; ++k) MGV_TRY(enqueue_decode_step(g, B, sa, att_out, Tf, s));
+  }
+  cudaError_t e1 = cudaEventRecord(g->ev_out, s);
+  cudaError_t e2 = cudaStreamWaitEvent(caller, g->ev_out, 0);
+  const int rc = read_err_flag(g, s, "gpt_generate");  // synchronises s
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
+  MGV_CHECK_CUDA(e1);
+  MGV_CHECK_CUDA(e2);
+  return rc;
+}
+
+long long gpt_last_launches(const Gpt* g) { return g ? g->launches : 0; }
+
+}  // namespace mgv

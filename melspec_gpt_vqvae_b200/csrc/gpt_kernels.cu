@@ -1,0 +1,585 @@
+// Non-GEMM kernels of the minGPT path.  See gpt_kernels.cuh.
+#include "gpt_kernels.cuh"
+
+namespace mgv {
+
+namespace {
+
+// ------------------------------------------------------------------ embedding
+__global__ void embed_kernel(const long long* __restrict__ idx, int R, int p_off, int idx_ld,
+                             const float* __restrict__ prefix_emb, const long long* __restrict__ cls,
+                             const float* __restrict__ embedder, int m, const float* __restrict__ tok_emb,
+                             const float* __restrict__ pos_emb, int C, int vocab, int class_size,
+                             float* __restrict__ x_out, int* __restrict__ err_flag) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x;  // b*R + r
+  const int b = row / R, p = p_off + (row - b * R);
+  const float* src;
+  if (p < m) {
+    if (prefix_emb) {
+      src = prefix_emb + (static_cast<long long>(b) * m + p) * C;
+    } else {
+      long long c = cls[b];
+      if (c < 0 || c >= class_size) {
+        if (err_flag) atomicExch(err_flag, 1);
+        c = 0;
+      }
+      src = embedder + c * C;
+    }
+  } else {
+    long long tok = idx[static_cast<long long>(b) * idx_ld + (p - m)];
+    if (tok < 0 || tok >= vocab) {
+      if (err_flag) atomicExch(err_flag, 2);
+      tok = 0;
+    }
+    src = tok_emb + tok * C;
+  }
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  const float4* p4 = reinterpret_cast<const float4*>(pos_emb + static_cast<long long>(p) * C);
+  float4* o4 = reinterpret_cast<float4*>(x_out + static_cast<long long>(row) * C);
+  for (int i = threadIdx.x; i < C / 4; i += blockDim.x) {
+    const float4 a = __ldg(s4 + i), q = __ldg(p4 + i);
+    o4[i] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm
+constexpr int LN_MAX_V4 = 16;  // C <= 2048
+
+__global__ void __launch_bounds__(128)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bia, int rows, int C,
+                 __nv_bfloat16* __restrict__ out, float* __restrict__ zero_buf, long long zero_count) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (zero_buf) {
+    const long long n4 = zero_count / 4;
+    float4* z4 = reinterpret_cast<float4*>(zero_buf);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+      z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= rows) return;
+  const int nv = C / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  float4 v[LN_MAX_V4];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V4; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      v[j] = x4[i];
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(C);
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V4; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(C) + 1e-5f);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(bia);
+  uint2* o2 = reinterpret_cast<uint2*>(out + static_cast<long long>(row) * C);
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V4; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      const float4 g = __ldg(w4 + i), be = __ldg(b4 + i);
+      const float a = (v[j].x - mean) * rstd * g.x + be.x;
+      const float b = (v[j].y - mean) * rstd * g.y + be.y;
+      const float c = (v[j].z - mean) * rstd * g.z + be.z;
+      const float d = (v[j].w - mean) * rstd * g.w + be.w;
+      o2[i] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ prefill attention
+constexpr int AP_ROWS = 32;       // query rows per CTA
+constexpr int AP_THREADS = 128;
+constexpr int AP_KSTRIDE = 33;    // 32-bit words per K/V row in smem (64 bf16 + 1 pad word)
+
+__global__ void __launch_bounds__(AP_THREADS)
+attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T, int nh, int n_unmasked,
+                    __nv_bfloat16* __restrict__ y, float* __restrict__ att, int att_T,
+                    __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache, int Tmax) {
+  extern __shared__ uint32_t ap_smem[];
+  const int bh = blockIdx.y;
+  const int b = bh / nh, h = bh - b * nh;
+  const int C = nh * GPT_HEAD_DIM;
+  const int q0 = blockIdx.x * AP_ROWS;
+  const int q_end = min(q0 + AP_ROWS, T);
+  const int kmax = (q0 < n_unmasked) ? max(q_end, min(n_unmasked, T)) : q_end;
+  uint32_t* Ks = ap_smem;                                    // [kmax][33]
+  uint32_t* Vs = Ks + static_cast<size_t>(GPT_MAX_T) * AP_KSTRIDE;  // [kmax][33]
+  float* sq = reinterpret_cast<float*>(Vs + static_cast<size_t>(GPT_MAX_T) * AP_KSTRIDE);  // [4][64]
+  float* sp = sq + 4 * GPT_HEAD_DIM;                         // [4][GPT_MAX_T]
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const bool write_cache = (kcache != nullptr) && (blockIdx.x == gridDim.x - 1);  // last block sees every key
+  for (int i = t; i < kmax * 8; i += AP_THREADS) {
+    const int row = i >> 3, part = i & 7;
+    const __nv_bfloat16* base = qkv + (static_cast<long long>(b) * T + row) * (3 * C) + h * GPT_HEAD_DIM + part * 8;
+    const uint4 kq = *reinterpret_cast<const uint4*>(base + C);
+    const uint4 vq = *reinterpret_cast<const uint4*>(base + 2 * C);
+    uint32_t* kd = Ks + row * AP_KSTRIDE + part * 4;
+    uint32_t* vd = Vs + row * AP_KSTRIDE + part * 4;
+    kd[0] = kq.x; kd[1] = kq.y; kd[2] = kq.z; kd[3] = kq.w;
+    vd[0] = vq.x; vd[1] = vq.y; vd[2] = vq.z; vd[3] = vq.w;
+    if (write_cache) {
+      const long long co = ((static_cast<long long>(b) * nh + h) * Tmax + row) * GPT_HEAD_DIM + part * 8;
+      *reinterpret_cast<uint4*>(kcache + co) = kq;
+      *reinterpret_cast<uint4*>(vcache + co) = vq;
+    }
+  }
+  __syncthreads();
+
+  const float scale = 1.0f / sqrtf(static_cast<float>(GPT_HEAD_DIM));   // minGPT.py:81
+  float* myq = sq + warp * GPT_HEAD_DIM;
+  float* myp = sp + warp * GPT_MAX_T;
+  const int nkb = (T + 31) / 32;
+  for (int r = warp; r < AP_ROWS; r += 4) {
+    const int row = q0 + r;
+    if (row >= T) break;
+    {
+      const uint32_t qw = *reinterpret_cast<const uint32_t*>(
+          qkv + (static_cast<long long>(b) * T + row) * (3 * C) + h * GPT_HEAD_DIM + 2 * lane);
+      const float2 qf = unpack_bf16x2(qw);
+      myq[2 * lane] = qf.x;
+      myq[2 * lane + 1] = qf.y;
+    }
+    __syncwarp();
+    float sc[GPT_MAX_T / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < GPT_MAX_T / 32; ++jj) {
+      sc[jj] = -INFINITY;
+      if (jj < nkb) {
+        const int key = jj * 32 + lane;
+        // mask[i][j] = tril, plus the unmasked prefix block (minGPT.py:65-68)
+        const bool allowed = key < T && (key <= row || (row < n_unmasked && key < n_unmasked));
+        if (allowed) {
+          const uint32_t* kr = Ks + key * AP_KSTRIDE;
+          float s = 0.f;
+#pragma unroll 8
+          for (int d2 = 0; d2 < 32; ++d2) {
+            const float2 kf = unpack_bf16x2(kr[d2]);
+            s = fmaf(myq[2 * d2], kf.x, s);
+            s = fmaf(myq[2 * d2 + 1], kf.y, s);
+          }
+          sc[jj] = s * scale;
+        }
+        mx = fmaxf(mx, sc[jj]);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < GPT_MAX_T / 32; ++jj) {
+      if (jj < nkb) {
+        sc[jj] = (sc[jj] == -INFINITY) ? 0.f : expf(sc[jj] - mx);
+        sum += sc[jj];
+      }
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float* arow = (att && row < att_T) ? att + ((static_cast<long long>(b) * nh + h) * att_T + row) * att_T : nullptr;
+#pragma unroll
+    for (int jj = 0; jj < GPT_MAX_T / 32; ++jj) {
+      if (jj < nkb) {
+        const int key = jj * 32 + lane;
+        const float p = sc[jj] * inv;
+        if (key < T) {
+          myp[key] = p;
+          if (arow && key < att_T && sc[jj] != 0.f) arow[key] = p;
+        }
+      }
+    }
+    __syncwarp();
+    const int kend = (row < n_unmasked) ? max(row + 1, min(n_unmasked, T)) : row + 1;
+    float a0 = 0.f, a1 = 0.f;
+    for (int key = 0; key < kend; ++key) {
+      const float p = myp[key];
+      const float2 vf = unpack_bf16x2(Vs[key * AP_KSTRIDE + lane]);
+      a0 = fmaf(p, vf.x, a0);
+      a1 = fmaf(p, vf.y, a1);
+    }
+    *reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b) * T + row) * C + h * GPT_HEAD_DIM + 2 * lane) =
+        pack_bf16x2(a0, a1);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ decode attention
+constexpr int AD_THREADS = 128;
+
+__global__ void __launch_bounds__(AD_THREADS)
+attn_decode_kernel(const float* __restrict__ qkv32, int nh, const int* __restrict__ pos_ptr,
+                   __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache, int Tmax,
+                   __nv_bfloat16* __restrict__ y, float* __restrict__ att_rows, int Tatt) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float sq[GPT_HEAD_DIM];
+  __shared__ float sk[GPT_HEAD_DIM];
+  __shared__ float sv[GPT_HEAD_DIM];
+  __shared__ float ss[GPT_MAX_T];
+  __shared__ float red[8];
+  __shared__ float sacc[4][GPT_HEAD_DIM];
+  const int bh = blockIdx.x;
+  const int b = bh / nh, h = bh - b * nh;
+  const int C = nh * GPT_HEAD_DIM;
+  const int pos = *pos_ptr;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  __nv_bfloat16* kc = kcache + (static_cast<long long>(b) * nh + h) * Tmax * GPT_HEAD_DIM;
+  __nv_bfloat16* vc = vcache + (static_cast<long long>(b) * nh + h) * Tmax * GPT_HEAD_DIM;
+
+  if (t < GPT_HEAD_DIM) {
+    const float* base = qkv32 + static_cast<long long>(b) * 3 * C + h * GPT_HEAD_DIM + t;
+    // q is rounded to bf16 like the prefill path (which stores q,k,v as bf16)
+    sq[t] = __bfloat162float(__float2bfloat16(base[0]));
+    const __nv_bfloat16 kb = __float2bfloat16(base[C]);
+    const __nv_bfloat16 vb = __float2bfloat16(base[2 * C]);
+    sk[t] = __bfloat162float(kb);
+    sv[t] = __bfloat162float(vb);
+    kc[static_cast<long long>(pos) * GPT_HEAD_DIM + t] = kb;
+    vc[static_cast<long long>(pos) * GPT_HEAD_DIM + t] = vb;
+  }
+  __syncthreads();
+
+  const float scale = 1.0f / sqrtf(static_cast<float>(GPT_HEAD_DIM));
+  float lmax = -INFINITY;
+  for (int j = t; j <= pos; j += AD_THREADS) {
+    float s = 0.f;
+    if (j < pos) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kc + static_cast<long long>(j) * GPT_HEAD_DIM);
+#pragma unroll
+      for (int part = 0; part < 8; ++part) {
+        const uint4 q4 = kr[part];
+        const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 kf = unpack_bf16x2(w[e]);
+          s = fmaf(sq[part * 8 + 2 * e], kf.x, s);
+          s = fmaf(sq[part * 8 + 2 * e + 1], kf.y, s);
+        }
+      }
+    } else {
+#pragma unroll 8
+      for (int d = 0; d < GPT_HEAD_DIM; ++d) s = fmaf(sq[d], sk[d], s);
+    }
+    s *= scale;
+    ss[j] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float lsum = 0.f;
+  for (int j = t; j <= pos; j += AD_THREADS) {
+    const float e = expf(ss[j] - mx);
+    ss[j] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red[4 + warp] = lsum;
+  __syncthreads();
+  const float inv = 1.0f / ((red[4] + red[5]) + (red[6] + red[7]));
+  if (att_rows) {
+    float* arow = att_rows + ((static_cast<long long>(b) * nh + h) * Tatt + pos) * Tatt;
+    if (pos < Tatt)
+      for (int j = t; j <= pos; j += AD_THREADS) arow[j] = ss[j] * inv;
+  }
+  // PV: lane -> dims (2*lane, 2*lane+1); warp -> keys j = warp, warp+4, ...
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = warp; j <= pos; j += 4) {
+    const float p = ss[j];
+    float2 vf;
+    if (j < pos)
+      vf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vc + static_cast<long long>(j) * GPT_HEAD_DIM + 2 * lane));
+    else
+      vf = make_float2(sv[2 * lane], sv[2 * lane + 1]);
+    a0 = fmaf(p, vf.x, a0);
+    a1 = fmaf(p, vf.y, a1);
+  }
+  sacc[warp][2 * lane] = a0;
+  sacc[warp][2 * lane + 1] = a1;
+  __syncthreads();
+  if (t < GPT_HEAD_DIM) {
+    const float o = ((sacc[0][t] + sacc[1][t]) + (sacc[2][t] + sacc[3][t])) * inv;
+    y[static_cast<long long>(b) * C + h * GPT_HEAD_DIM + t] = __float2bfloat16(o);
+  }
+}
+
+// ------------------------------------------------------------------ GELU (split-K FC1 path)
+__global__ void gelu_bf16_kernel(const float* __restrict__ h32, long long n4, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const float4* i4 = reinterpret_cast<const float4*>(h32);
+  uint2* o2 = reinterpret_cast<uint2*>(out);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = i4[i];
+    o2[i] = make_uint2(pack_bf16x2(gelu_erf(v.x), gelu_erf(v.y)), pack_bf16x2(gelu_erf(v.z), gelu_erf(v.w)));
+  }
+}
+
+// ------------------------------------------------------------------ final LN + head + top-k + sample
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+// Philox4x32-10 -> uniform in [0,1) with 24 bits
+__device__ float philox_uniform(unsigned long long seed, uint32_t ctr0, uint32_t ctr1) {
+  uint32_t c[4] = {ctr0, ctr1, 0u, 0u};
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return static_cast<float>(c[0] >> 8) * (1.0f / 16777216.0f);
+}
+
+constexpr int SAMPLE_THREADS = 256;
+constexpr int SAMPLE_MAX_V = 1024;
+
+__device__ float block_reduce(float v, float* red, bool is_max) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < SAMPLE_THREADS / 32; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+sample_step_kernel(const SampleArgs a) {
+  unsigned int* done_counter = a.done_counter;
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ float sm_s[];
+  float* sx = sm_s;            // [C]
+  float* sl = sx + a.C;        // [V]
+  __shared__ float red[SAMPLE_THREADS / 32];
+  __shared__ int s_tok;
+  const int b = blockIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int pos = *a.pos_ptr;
+
+  // ---- ln_f (minGPT.py:186)
+  const float* xr = a.x + static_cast<long long>(b) * a.C;
+  float s = 0.f;
+  for (int i = t; i < a.C; i += SAMPLE_THREADS) {
+    const float v = xr[i];
+    sx[i] = v;
+    s += v;
+  }
+  const float mean = block_reduce(s, red, false) / static_cast<float>(a.C);
+  float ssq = 0.f;
+  for (int i = t; i < a.C; i += SAMPLE_THREADS) {
+    const float d = sx[i] - mean;
+    ssq += d * d;
+  }
+  const float rstd = rsqrtf(block_reduce(ssq, red, false) / static_cast<float>(a.C) + 1e-5f);
+  for (int i = t; i < a.C; i += SAMPLE_THREADS) {
+    // rounded to bf16 like the prefill path, which feeds the head GEMM with bf16 activations
+    sx[i] = __bfloat162float(__float2bfloat16((sx[i] - mean) * rstd * __ldg(a.lnf_w + i) + __ldg(a.lnf_b + i)));
+  }
+  __syncthreads();
+
+  // ---- head (no bias, minGPT.py:149,188) ; logits / temperature (:346)
+  const int nchunk = a.C / 8;
+  for (int v = warp; v < a.V; v += SAMPLE_THREADS / 32) {
+    const uint4* wr = reinterpret_cast<const uint4*>(a.whead + static_cast<long long>(v) * a.C);
+    float acc = 0.f;
+    for (int ch = lane; ch < nchunk; ch += 32) {
+      const uint4 q = __ldg(wr + ch);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 wf = unpack_bf16x2(w[e]);
+        acc = fmaf(sx[ch * 8 + 2 * e], wf.x, acc);
+        acc = fmaf(sx[ch * 8 + 2 * e + 1], wf.y, acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float l = __fdiv_rn(acc, a.temperature);
+      sl[v] = l;
+      if (a.logits_out) a.logits_out[static_cast<long long>(b) * a.V + v] = l;
+    }
+  }
+  __syncthreads();
+
+  // ---- top_k_logits (minGPT.py:287-291): everything below the k-th largest value -> -inf (ties kept)
+  if (a.top_k > 0 && a.top_k < a.V) {
+    float cand = INFINITY;
+    for (int i = t; i < a.V; i += SAMPLE_THREADS) {
+      const float li = sl[i];
+      int greater = 0;
+      for (int j = 0; j < a.V; ++j) greater += (sl[j] > li) ? 1 : 0;
+      if (greater < a.top_k) cand = fminf(cand, li);
+    }
+    const float thr = -block_reduce(-cand, red, true);
+    __syncthreads();
+    for (int i = t; i < a.V; i += SAMPLE_THREADS)
+      if (sl[i] < thr) sl[i] = -INFINITY;
+    __syncthreads();
+  }
+
+  // ---- softmax (:351)
+  float lm = -INFINITY;
+  for (int i = t; i < a.V; i += SAMPLE_THREADS) lm = fmaxf(lm, sl[i]);
+  const float mx = block_reduce(lm, red, true);
+  float ls = 0.f;
+  for (int i = t; i < a.V; i += SAMPLE_THREADS) {
+    const float e = (sl[i] == -INFINITY) ? 0.f : expf(sl[i] - mx);
+    sl[i] = e;
+    ls += e;
+  }
+  const float total = block_reduce(ls, red, false);
+  __syncthreads();
+
+  // ---- multinomial(probs, 1) (:354) or topk(probs, 1) (:356)
+  if (t == 0) {
+    int tok = 0;
+    if (a.do_sample) {
+      const float u = philox_uniform(a.seed, static_cast<uint32_t>(pos), static_cast<uint32_t>(b));
+      const float target = u * total;
+      float cum = 0.f;
+      int last_nonzero = 0;
+      tok = -1;
+      for (int i = 0; i < a.V; ++i) {
+        const float p = sl[i];
+        if (p > 0.f) last_nonzero = i;
+        cum += p;
+        if (tok < 0 && cum > target && p > 0.f) tok = i;
+      }
+      if (tok < 0) tok = last_nonzero;
+    } else {
+      float best = -1.f;
+      for (int i = 0; i < a.V; ++i)
+        if (sl[i] > best) {
+          best = sl[i];
+          tok = i;
+        }
+    }
+    s_tok = tok;
+    const int slot = pos + 1 - a.m;
+    if (slot >= 0 && slot < a.tokens_ld) a.tokens[static_cast<long long>(b) * a.tokens_ld + slot] = tok;
+  }
+  __syncthreads();
+  const int tok = s_tok;
+
+  // ---- embedding of the sampled token for the next position (minGPT.py:170-180)
+  if (a.x_next && pos + 1 < a.block_size) {
+    const float* te = a.tok_emb + static_cast<long long>(tok) * a.C;
+    const float* pe = a.pos_emb + static_cast<long long>(pos + 1) * a.C;
+    float* xn = a.x_next + static_cast<long long>(b) * a.C;
+    for (int i = t; i < a.C; i += SAMPLE_THREADS) xn[i] = __ldg(te + i) + __ldg(pe + i);
+  }
+
+  // ---- the last CTA to finish advances the position (every CTA read *pos_ptr before arriving)
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(done_counter, 1u);
+    if (done == gridDim.x - 1) {
+      *a.pos_ptr = pos + 1;
+      *done_counter = 0u;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace
+
+// ====================================================================== host wrappers
+int gpt_embed(const long long* idx, int B, int R, int p_off, int idx_ld, const float* prefix_emb, const long long* cls,
+              const float* embedder, int m, const float* tok_emb, const float* pos_emb, int C, int vocab,
+              int class_size, float* x_out, int* err_flag, cudaStream_t s, bool pdl) {
+  MGV_REQUIRE(C % 4 == 0, "embed: C=%d", C);
+  MGV_REQUIRE(p_off >= m || prefix_emb || (cls && embedder), "embed: prefix of length %d without embeddings", m);
+  MGV_REQUIRE(p_off + R <= m || idx, "embed: null idx");
+  if (B * R == 0) return MGV_OK;
+  LaunchCfg lc(dim3(B * R), dim3(256), 0, s, pdl);
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, embed_kernel, idx, R, p_off, idx_ld, prefix_emb, cls, embedder, m, tok_emb,
+                                    pos_emb, C, vocab, class_size, x_out, err_flag));
+  return MGV_OK;
+}
+
+int gpt_layernorm(const float* x, const float* w, const float* b, int rows, int C, __nv_bfloat16* out, float* zero_buf,
+                  long long zero_count, cudaStream_t s, bool pdl) {
+  MGV_REQUIRE(C % 4 == 0 && C <= LN_MAX_V4 * 128, "layernorm: C=%d unsupported", C);
+  MGV_REQUIRE(zero_count % 4 == 0, "layernorm: zero_count");
+  if (rows == 0) return MGV_OK;
+  LaunchCfg lc(dim3(ceil_div(rows, 4)), dim3(128), 0, s, pdl);
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, layernorm_kernel, x, w, b, rows, C, out, zero_buf, zero_count));
+  return MGV_OK;
+}
+
+int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_unmasked, __nv_bfloat16* y, float* att,
+                          int att_T, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int Tmax, cudaStream_t s) {
+  MGV_REQUIRE(T >= 1 && T <= GPT_MAX_T, "attention: T=%d exceeds %d", T, GPT_MAX_T);
+  if (B == 0) return MGV_OK;
+  const size_t smem = (2 * static_cast<size_t>(GPT_MAX_T) * AP_KSTRIDE) * 4 + (4 * GPT_HEAD_DIM + 4 * GPT_MAX_T) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(T, AP_ROWS), B * nh);
+  attn_prefill_kernel<<<grid, AP_THREADS, smem, s>>>(qkv, B, T, nh, n_unmasked, y, att, att_T, kcache, vcache, Tmax);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int gpt_attention_decode(const float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
+                         __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, cudaStream_t s,
+                         bool pdl) {
+  MGV_REQUIRE(Tmax <= GPT_MAX_T, "attention: Tmax=%d exceeds %d", Tmax, GPT_MAX_T);
+  if (B == 0) return MGV_OK;
+  LaunchCfg lc(dim3(B * nh), dim3(AD_THREADS), 0, s, pdl);
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_kernel, qkv32, nh, pos_ptr, kcache, vcache, Tmax, y, att_rows,
+                                    Tatt));
+  return MGV_OK;
+}
+
+int gpt_gelu_bf16(const float* h32, long long n, __nv_bfloat16* out, cudaStream_t s, bool pdl) {
+  MGV_REQUIRE(n % 4 == 0, "gelu: n");
+  if (n == 0) return MGV_OK;
+  const long long n4 = n / 4;
+  int blocks = static_cast<int>((n4 + 255) / 256);
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  LaunchCfg lc(dim3(blocks), dim3(256), 0, s, pdl);
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gelu_bf16_kernel, h32, n4, out));
+  return MGV_OK;
+}
+
+int gpt_sample_step(const SampleArgs& a, cudaStream_t s, bool pdl) {
+  MGV_REQUIRE(a.done_counter && a.pos_ptr, "sample: null state pointers");
+  MGV_REQUIRE(a.V >= 1 && a.V <= SAMPLE_MAX_V, "sample: vocab=%d unsupported (<= %d)", a.V, SAMPLE_MAX_V);
+  MGV_REQUIRE(a.C % 8 == 0, "sample: C=%d", a.C);
+  MGV_REQUIRE(a.temperature > 0.f, "sample: temperature must be > 0");
+  if (a.B == 0) return MGV_OK;
+  const size_t smem = (static_cast<size_t>(a.C) + a.V) * 4;
+  LaunchCfg lc(dim3(a.B), dim3(SAMPLE_THREADS), smem, s, pdl);
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, sample_step_kernel, a));
+  return MGV_OK;
+}
+
+}  // namespace mgv

@@ -1,0 +1,62 @@
+// Non-GEMM kernels of the minGPT path (embedding, LayerNorm, attention, GELU, fused
+// final-LN + head + top-k + sampling).  reference: transformer/minGPT.py:45-199, 287-360.
+#pragma once
+#include "mgv_common.cuh"
+
+namespace mgv {
+
+constexpr int GPT_HEAD_DIM = 64;   // n_embd / n_head for every reference config
+constexpr int GPT_MAX_T = 288;     // >= block_size (266), multiple of 32
+
+// x[b,t,:] = (t < m ? prefix : tok_emb[idx[b,t-m]]) + pos_emb[t]            (minGPT.py:170-180)
+// prefix is either prefix_emb[b,t,:] (float embeddings) or embedder[cls[b]] (GPTClass, :210)
+// Rows p = p_off .. p_off+R-1 of every sequence are produced: x_out is [B, R, C].
+int gpt_embed(const long long* idx, int B, int R, int p_off, int idx_ld, const float* prefix_emb, const long long* cls,
+              const float* embedder, int m, const float* tok_emb, const float* pos_emb, int C, int vocab,
+              int class_size, float* x_out, int* err_flag, cudaStream_t s, bool pdl);
+
+// LayerNorm (eps 1e-5, affine) fp32 rows -> bf16 rows; optionally zero-fills `zero_buf`
+// (the split-K accumulation buffer of the GEMM that follows).
+int gpt_layernorm(const float* x, const float* w, const float* b, int rows, int C, __nv_bfloat16* out, float* zero_buf,
+                  long long zero_count, cudaStream_t s, bool pdl);
+
+// Causal (or prefix-unmasked) self-attention over a whole sequence (prefill / teacher forcing).
+// qkv: bf16 [B*T, 3C] = [q | k | v]; y: bf16 [B*T, C];
+// att (optional): fp32 [B, nh, att_T, att_T], PRE-ZEROED by the caller; only unmasked entries are written;
+// kcache/vcache (optional): bf16 [B, nh, Tmax, 64] receive K and V of positions 0..T-1.
+int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_unmasked, __nv_bfloat16* y, float* att,
+                          int att_T, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int Tmax, cudaStream_t s);
+
+// One decode position: q,k,v fp32 [B, 3C] for position *pos_ptr; appends k,v to the cache and
+// attends over positions 0..pos.  att_rows (optional): fp32 [B, nh, Tatt, Tatt] pre-zeroed; entries 0..pos of row pos are written.
+int gpt_attention_decode(const float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
+                         __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, cudaStream_t s,
+                         bool pdl);
+
+// h = gelu_erf(h32) as bf16 (split-K FC1 path)
+int gpt_gelu_bf16(const float* h32, long long n, __nv_bfloat16* out, cudaStream_t s, bool pdl);
+
+struct SampleArgs {
+  const float* x;          // [B, C] final residual stream of the step
+  const float* lnf_w;
+  const float* lnf_b;
+  const __nv_bfloat16* whead;  // [V, C]
+  int B, C, V;
+  float temperature;
+  int top_k;               // 0 = no top-k
+  int do_sample;           // 0 = greedy (torch.topk(probs, 1)), 1 = multinomial
+  unsigned long long seed;
+  int* pos_ptr;            // device: position of the row just processed; incremented here
+  long long* tokens;       // [B, tokens_ld]; token for sequence slot (pos - m + 1) ... see kernel
+  int tokens_ld;
+  int m;                   // prefix length (cond_size)
+  const float* tok_emb;
+  const float* pos_emb;
+  int block_size;
+  float* x_next;           // [B, C]: embedding of the sampled token at position pos+1
+  float* logits_out;       // optional [B, V]: logits of this step (after temperature, before top-k)
+  unsigned int* done_counter;  // device scratch (zero-initialised) used to advance *pos_ptr once per step
+};
+int gpt_sample_step(const SampleArgs& a, cudaStream_t s, bool pdl);
+
+}  // namespace mgv
