@@ -67,7 +67,9 @@ def argmin_exact(z_bchw: np.ndarray, codebook: np.ndarray, threads: int = 0):
     z3 = z.reshape(B, D, HW)
 
     def run(lo, hi):
-        lib.vq_argmin_oracle(_p(z3[lo:hi]), _p(cb), hi - lo, D, HW, K, _p(idx[lo * HW:hi * HW]), _p(dmin[lo * HW:hi * HW]))
+        lo, hi = int(lo), int(hi)
+        lib.vq_argmin_oracle(_p(z3[lo:hi]), _p(cb), hi - lo, int(D), HW, int(K), _p(idx[lo * HW:hi * HW]),
+                             _p(dmin[lo * HW:hi * HW]))
 
     bounds = np.linspace(0, B, threads + 1).astype(int)
     with ThreadPoolExecutor(max_workers=threads) as ex:
@@ -83,7 +85,7 @@ def distances_exact(z_bchw: np.ndarray, codebook: np.ndarray) -> np.ndarray:
     HW = int(np.prod(z.shape[2:]))
     cb = np.ascontiguousarray(codebook, dtype=np.float32)
     dist = np.empty((B * HW, cb.shape[0]), dtype=np.float32)
-    lib.vq_distances_oracle(_p(z.reshape(B, D, HW)), _p(cb), B, D, HW, cb.shape[0], _p(dist))
+    lib.vq_distances_oracle(_p(z.reshape(B, D, HW)), _p(cb), int(B), int(D), HW, int(cb.shape[0]), _p(dist))
     return dist
 
 

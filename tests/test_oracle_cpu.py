@@ -1,0 +1,147 @@
+"""CPU: the oracle (oracle/*.py, oracle/vq_oracle.c) against the golden fixtures produced by the
+UNMODIFIED reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from make_golden import GPT_SMALL, GPT_SMALL_UNMASKED, gpt_inputs, vq_inputs
+from melspec_gpt_vqvae_b200 import synthetic
+from oracle import gpt_oracle, vq_oracle, vqvae_oracle
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("case", ["trained", "default_init", "ties", "small"])
+def test_vq_oracle_vs_reference(golden_dir, case):
+    g = load(golden_dir, "vq_%s.npz" % case)
+    z, cb = vq_inputs(case)
+    z, cb = z.numpy(), cb.numpy()
+    ref_idx = g["idx"].astype(np.int64).reshape(-1)
+    # (1) fixed-order C restatement: equal to the reference except classified near-ties
+    idx, dmin = vq_oracle.argmin_exact(z, cb)
+    dist = vq_oracle.distances_exact(z, cb)
+    assert np.array_equal(dist.argmin(1), idx)                      # first-index argmin
+    assert np.array_equal(dist[np.arange(idx.size), idx], dmin)
+    rep = vq_oracle.classify_mismatches(dist, idx, ref_idx, ulps=16)
+    print(case, rep)
+    assert rep["n_real"] == 0, rep
+    if case == "trained":
+        assert rep["n_mismatch"] == 0, rep
+    if case == "ties":
+        # exact duplicates (code j and j+64): the lower index must win
+        assert (idx < 64).all()
+    # (2) formula restatement in numpy: remaining outputs on the reference's own indices
+    loss, quant, (perp, enc, enc_idx) = vq_oracle.forward_numpy(z, cb, 0.25, indices=ref_idx)
+    np.testing.assert_allclose(loss, g["loss"], rtol=1e-6)
+    np.testing.assert_allclose(perp, g["perplexity"], rtol=1e-5)
+    np.testing.assert_allclose(quant, g["quantized"], rtol=0, atol=1e-7)   # straight-through rounding <= 1 ulp
+    np.testing.assert_array_equal(enc.sum(1), g["enc_rowsum"])
+    np.testing.assert_array_equal(enc.sum(0), g["enc_colsum"])
+    # and with its own argmin
+    _, _, (_, _, own_idx) = vq_oracle.forward_numpy(z, cb, 0.25)
+    rep2 = vq_oracle.classify_mismatches(dist, own_idx.reshape(-1), ref_idx, ulps=16)
+    assert rep2["n_real"] == 0, rep2
+    # (3) get_codebook_entry: pure gather, exact
+    B, D = z.shape[0], z.shape[1]
+    entry = vq_oracle.get_codebook_entry_numpy(ref_idx, cb, (B, z.shape[2], z.shape[3], D))
+    np.testing.assert_array_equal(entry, g["entry"])
+    np.testing.assert_array_equal(vq_oracle.get_codebook_entry_numpy(ref_idx[:7], cb, None), g["entry_flat"])
+
+
+def test_vq_oracle_empty_and_single():
+    cb = np.random.RandomState(0).randn(128, 256).astype(np.float32)
+    idx, dmin = vq_oracle.argmin_exact(np.zeros((0, 256, 5, 53), np.float32), cb)
+    assert idx.shape == (0,)
+    z = cb[5].reshape(1, 256, 1, 1)
+    idx, dmin = vq_oracle.argmin_exact(z, cb)
+    assert idx.tolist() == [5]
+
+
+@pytest.mark.parametrize("name,B,T", [("small", 3, 265), ("small_short", 2, 17)])
+def test_gpt_oracle_small(golden_dir, name, B, T):
+    g = load(golden_dir, "gpt_%s.npz" % name)
+    cfg = gpt_oracle.GPTCfg(**GPT_SMALL)
+    sd = synthetic.synthetic_gpt_state_dict(GPT_SMALL, seed=101, perturb=True)
+    x, c = gpt_inputs(B, T, 128, 8, seed=7)
+    logits, _, att = gpt_oracle.gptclass_forward(sd, cfg, x[:, :-1], c)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(att.numpy(), g["att"], rtol=1e-4, atol=1e-6)
+
+
+def test_gpt_oracle_unmasked_prefix_embedding(golden_dir):
+    g = load(golden_dir, "gpt_small_unmasked.npz")
+    cfg = gpt_oracle.GPTCfg(**GPT_SMALL_UNMASKED)
+    sd = synthetic.synthetic_gpt_state_dict(GPT_SMALL_UNMASKED, seed=102, perturb=True)
+    x, _ = gpt_inputs(2, 40, 128, 0, seed=8)
+    emb = torch.randn(2, 1, 128, generator=torch.Generator().manual_seed(9)) * 0.1
+    logits, _, att = gpt_oracle.gpt_forward(sd, cfg, x, embeddings=emb)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(att.numpy(), g["att"], rtol=1e-4, atol=1e-6)
+
+
+def test_gpt_oracle_greedy_sample(golden_dir):
+    g = load(golden_dir, "gpt_small_greedy.npz")
+    cfg = gpt_oracle.GPTCfg(**GPT_SMALL)
+    sd = synthetic.synthetic_gpt_state_dict(GPT_SMALL, seed=101, perturb=True)
+    sd["head.weight"] = sd["head.weight"] * 8.0
+    c = torch.tensor([[3], [5]])
+    ks = []
+    xs, att = gpt_oracle.sample(sd, cfg, torch.zeros(2, 0, dtype=torch.long), c, steps=40, callback=ks.append)
+    assert ks == list(range(40))
+    np.testing.assert_array_equal(xs.numpy(), g["tokens"][:, :40])
+    # teacher-forced logits on the reference's tokens
+    toks = torch.from_numpy(g["tokens"].astype(np.int64))
+    logits, target = gpt_oracle.lit_forward(sd, cfg, toks, c)
+    np.testing.assert_allclose(logits.numpy(), g["logits_tf"], rtol=1e-4, atol=1e-4)
+    assert torch.equal(target, toks)
+    # half-prompt continuation with temperature and top-k
+    g2 = load(golden_dir, "gpt_small_greedy_half.npz")
+    xs2, att2 = gpt_oracle.sample(sd, cfg, toks[:, :132], c, steps=20, temperature=0.7, top_k=100)
+    np.testing.assert_array_equal(xs2.numpy(), g2["tokens"][:, :152])
+
+
+def test_block_size_assert():
+    cfg = gpt_oracle.GPTCfg(**GPT_SMALL)
+    sd = synthetic.synthetic_gpt_state_dict(GPT_SMALL, seed=101)
+    with pytest.raises(AssertionError):
+        gpt_oracle.gptclass_forward(sd, cfg, torch.zeros(1, 266, dtype=torch.long), torch.zeros(1, 1, dtype=torch.long))
+
+
+def test_topk_and_code_reader(golden_dir):
+    g = load(golden_dir, "topk.npz")
+    lg = torch.from_numpy(g["logits"])
+    np.testing.assert_array_equal(gpt_oracle.top_k_logits(lg, 100).numpy(), g["out100"])
+    np.testing.assert_array_equal(gpt_oracle.top_k_logits(lg, 1).numpy(), g["out1"])
+    c = load(golden_dir, "code_reader.npz")
+    fwd, bwd = gpt_oracle.make_idx(5, 53)
+    np.testing.assert_array_equal(fwd, c["fwd"])
+    np.testing.assert_array_equal(bwd, c["bwd"])
+    x = np.arange(2 * 265).reshape(2, 265)
+    np.testing.assert_array_equal(gpt_oracle.code_reader(gpt_oracle.code_reader(x), reverse=True), x)
+    assert fwd[:6].tolist() == [0, 53, 106, 159, 212, 1]
+
+
+def test_gpt_oracle_vas_full(golden_dir):
+    g = load(golden_dir, "gpt_vas.npz")
+    cfg = gpt_oracle.GPTCfg(**synthetic.GPT_VAS)
+    sd = synthetic.synthetic_gpt_state_dict(synthetic.GPT_VAS, seed=783435, perturb=True)
+    x, c = gpt_inputs(2, 265, 128, 8, seed=0)
+    logits, _, att = gpt_oracle.gptclass_forward(sd, cfg, x[:, :-1], c)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(att[:, :, ::33].numpy(), g["att_rows"], rtol=1e-4, atol=1e-6)
+
+
+def test_vqvae_oracle(golden_dir):
+    g = load(golden_dir, "vqvae.npz")
+    sd = synthetic.synthetic_vqvae_state_dict(128, 256, seed=783435, perturb=True)
+    gen = torch.Generator().manual_seed(21)
+    codes = torch.randint(0, 128, (1, 265), generator=gen)
+    mel = vqvae_oracle.decode_codes(sd, codes, 1)
+    np.testing.assert_allclose(mel.numpy(), g["mel"], rtol=1e-4, atol=1e-5)
+    melin = torch.rand(1, 1, 80, 848, generator=gen) * 2 - 1
+    z = vqvae_oracle.encode(sd, melin)
+    np.testing.assert_allclose(z.numpy(), g["z"], rtol=1e-4, atol=1e-5)
