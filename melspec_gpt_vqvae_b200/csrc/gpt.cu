@@ -453,8 +453,8 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   MGV_TRY(check_loaded(g));
   MGV_TRY(check_qkv_complete(g));
   MGV_REQUIRE(B >= 0 && t0 >= 0 && steps >= 0, "gpt_generate: negative sizes");
-  MGV_REQUIRE(m >= 1, "gpt_generate: needs a conditioning prefix (class token or embedding)");
-  MGV_REQUIRE(prefix_emb || (cls && g->loaded[2]), "gpt_generate: prefix without embeddings / embedder");
+  MGV_REQUIRE(m >= 0 && m + t0 >= 1, "gpt_generate: empty context (needs a conditioning prefix or a prompt)");
+  MGV_REQUIRE(m == 0 || prefix_emb || (cls && g->loaded[2]), "gpt_generate: prefix without embeddings / embedder");
   MGV_REQUIRE(g->Vout == g->V, "gpt_generate: head output %d != vocab %d", g->Vout, g->V);
   MGV_REQUIRE(top_k >= 0 && top_k <= g->V, "gpt_generate: top_k=%d out of range for vocab %d", top_k, g->V);
   // assert x.size(1) + cond_size <= block_size at every step (minGPT.py:336)

@@ -1,1 +1,542 @@
-// placeholder
+// Non-GEMM kernels of the VQVAE encoder / decoder.  See vqvae_kernels.cuh.
+#include "vqvae_kernels.cuh"
+
+namespace mgv {
+
+namespace {
+
+constexpr float GN_EPS = 1e-6f;   // Normalize(): GroupNorm(32, C, eps=1e-6)  (big_model_attn_gan.py:139-140)
+constexpr int GN_GROUPS = 32;
+
+inline int grid_for(long long items, int threads, int per_sm = 8) {
+  long long b = (items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// ------------------------------------------------------------------ weight prep
+__global__ void repack_conv_kernel(const float* __restrict__ src, int Cout, int Cin, int KK,
+                                   __nv_bfloat16* __restrict__ dst) {
+  const long long total = static_cast<long long>(Cout) * Cin * KK;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const long long r = i / Cin;
+    const int tap = static_cast<int>(r % KK);
+    const int co = static_cast<int>(r / KK);
+    dst[i] = __float2bfloat16(src[(static_cast<long long>(co) * Cin + ci) * KK + tap]);
+  }
+}
+
+__global__ void gather_table_kernel(const float* __restrict__ codebook, const float* __restrict__ wpq,
+                                    const float* __restrict__ bpq, int K, int Cin, int Cout,
+                                    __nv_bfloat16* __restrict__ table) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * Cout) return;
+  const int co = i % Cout, k = i / Cout;
+  float acc = 0.f;
+  for (int c = 0; c < Cin; ++c) acc = fmaf(codebook[static_cast<size_t>(k) * Cin + c], wpq[static_cast<size_t>(co) * Cin + c], acc);
+  table[i] = __float2bfloat16(acc + bpq[co]);
+}
+
+__global__ void gather_rows_kernel(const long long* __restrict__ idx, const uint4* __restrict__ table, long long n,
+                                   int C8, int K, uint4* __restrict__ out, int* __restrict__ bad_flag) {
+  const long long total = n * C8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / C8;
+    const int c8 = static_cast<int>(i - row * C8);
+    long long code = idx[row];
+    if (code < 0 || code >= K) {
+      if (bad_flag) atomicExch(bad_flag, 1);
+      code = 0;
+    }
+    out[i] = __ldg(table + code * C8 + c8);
+  }
+}
+
+// ------------------------------------------------------------------ layout changes
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, int N, int C, int HW,
+                                         __nv_bfloat16* __restrict__ out) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long r = i / C;
+    const int p = static_cast<int>(r % HW);
+    const long long n = r / HW;
+    out[i] = __float2bfloat16(in[(n * C + c) * HW + p]);
+  }
+}
+
+__global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ in, int N, int C, int HW, float* __restrict__ out) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(i % HW);
+    const long long r = i / HW;
+    const int c = static_cast<int>(r % C);
+    const long long n = r / C;
+    out[i] = in[(n * HW + p) * C + c];
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm
+// grid (chunks, N); block 256; every thread owns a fixed channel octet (256 % (C/8) == 0)
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const uint4* __restrict__ x, int HW, int C, float* __restrict__ sums) {
+  __shared__ float sh[GN_GROUPS * 2];
+  if (threadIdx.x < GN_GROUPS * 2) sh[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int C8 = C / 8;
+  const int n = blockIdx.y;
+  const long long items = static_cast<long long>(HW) * C8;
+  const uint4* xn = x + static_cast<long long>(n) * items;
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < items;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 v = __ldg(xn + i);
+    float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    s0 += (a.x + a.y) + (b.x + b.y);
+    q0 += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
+    s1 += (c.x + c.y) + (d.x + d.y);
+    q1 += (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+  }
+  const int c8 = threadIdx.x % C8;
+  const int gch = C / GN_GROUPS;  // 4, 8, 16
+  const int g0 = (c8 * 8) / gch, g1 = (c8 * 8 + 4) / gch;
+  atomicAdd(&sh[2 * g0], s0);
+  atomicAdd(&sh[2 * g0 + 1], q0);
+  atomicAdd(&sh[2 * g1], s1);
+  atomicAdd(&sh[2 * g1 + 1], q1);
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS * 2) atomicAdd(&sums[static_cast<long long>(n) * GN_GROUPS * 2 + threadIdx.x], sh[threadIdx.x]);
+}
+
+__device__ __forceinline__ void gn_mean_rstd(const float* __restrict__ sums, long long n, int g, float inv_cnt,
+                                             float& mean, float& rstd) {
+  const float s = sums[(n * GN_GROUPS + g) * 2], q = sums[(n * GN_GROUPS + g) * 2 + 1];
+  mean = s * inv_cnt;
+  const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+  rstd = rsqrtf(var + GN_EPS);
+}
+
+__device__ __forceinline__ uint4 gn_apply8(const uint4 v, float m0, float r0, float m1, float r1,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta, int c0,
+                                            bool do_swish) {
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+  const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+  const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+  const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+  float o[8];
+  o[0] = (a.x - m0) * r0 * ga.x + ba.x;
+  o[1] = (a.y - m0) * r0 * ga.y + ba.y;
+  o[2] = (b.x - m0) * r0 * ga.z + ba.z;
+  o[3] = (b.y - m0) * r0 * ga.w + ba.w;
+  o[4] = (c.x - m1) * r1 * gb.x + bb.x;
+  o[5] = (c.y - m1) * r1 * gb.y + bb.y;
+  o[6] = (d.x - m1) * r1 * gb.z + bb.z;
+  o[7] = (d.y - m1) * r1 * gb.w + bb.w;
+  if (do_swish) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = swish(o[e]);
+  }
+  return make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
+                const float* __restrict__ beta, long long total, int HW, int C, int do_swish, uint4* __restrict__ y) {
+  const int C8 = C / 8;
+  const int gch = C / GN_GROUPS;
+  const float inv_cnt = 1.0f / (static_cast<float>(HW) * static_cast<float>(gch));
+  const long long per_img = static_cast<long long>(HW) * C8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / per_img;
+    const int c8 = static_cast<int>(i % C8);
+    const int c0 = c8 * 8;
+    float m0, r0, m1, r1;
+    gn_mean_rstd(sums, n, c0 / gch, inv_cnt, m0, r0);
+    gn_mean_rstd(sums, n, (c0 + 4) / gch, inv_cnt, m1, r1);
+    y[i] = gn_apply8(__ldg(x + i), m0, r0, m1, r1, gamma, beta, c0, do_swish != 0);
+  }
+}
+
+// ------------------------------------------------------------------ nearest 2x upsample
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int N, int H, int W, int C8, uint4* __restrict__ y) {
+  const long long total = static_cast<long long>(N) * (2 * H) * (2 * W) * C8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    long long r = i / C8;
+    const int xo = static_cast<int>(r % (2 * W));
+    r /= (2 * W);
+    const int yo = static_cast<int>(r % (2 * H));
+    const long long n = r / (2 * H);
+    y[i] = __ldg(x + ((n * H + (yo >> 1)) * W + (xo >> 1)) * C8 + c8);
+  }
+}
+
+// ------------------------------------------------------------------ spatial self-attention (AttnBlock :434-446)
+constexpr int SA_ROWS = 32;
+constexpr int SA_KCH = 32;
+constexpr int SA_THREADS = 256;
+
+template <int C>
+__global__ void __launch_bounds__(SA_THREADS)
+spatial_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bfloat16* __restrict__ o) {
+  constexpr int RS = C / 2 + 4;            // row stride in 32-bit words (16-byte aligned rows, conflict-free LDS.128)
+  extern __shared__ __align__(16) uint32_t sa_smem[];
+  uint32_t* Qs = sa_smem;                  // [32][RS]
+  uint32_t* KVs = Qs + SA_ROWS * RS;       // [32][RS]
+  const int Tpad = ((T + SA_KCH - 1) / SA_KCH) * SA_KCH;
+  const int SW = Tpad + 1;
+  float* Ss = reinterpret_cast<float*>(KVs + SA_KCH * RS);  // [32][SW]
+
+  const int n = blockIdx.y;
+  const int q0 = blockIdx.x * SA_ROWS;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const __nv_bfloat16* base = qkv + static_cast<long long>(n) * T * (3 * C);
+  constexpr int V8 = C / 8;                // uint4 per row
+
+  // ---- Q tile
+  for (int i = t; i < SA_ROWS * V8; i += SA_THREADS) {
+    const int r = i / V8, c8 = i - r * V8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q0 + r < T) v = *reinterpret_cast<const uint4*>(base + static_cast<long long>(q0 + r) * (3 * C) + c8 * 8);
+    *reinterpret_cast<uint4*>(Qs + r * RS + c8 * 4) = v;
+  }
+  const float scale = rsqrtf(static_cast<float>(C));   // int(c) ** (-0.5)   (:439)
+  const int qi = t >> 3, sub = t & 7;
+  const int nchunks = Tpad / SA_KCH;
+
+  // ---- scores S = Q K^T * scale
+  for (int kc = 0; kc < nchunks; ++kc) {
+    __syncthreads();
+    for (int i = t; i < SA_KCH * V8; i += SA_THREADS) {
+      const int r = i / V8, c8 = i - r * V8;
+      const int key = kc * SA_KCH + r;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (key < T) v = *reinterpret_cast<const uint4*>(base + static_cast<long long>(key) * (3 * C) + C + c8 * 8);
+      *reinterpret_cast<uint4*>(KVs + r * RS + c8 * 4) = v;
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};   // keys sub, sub+8, sub+16, sub+24
+#pragma unroll 4
+    for (int w4 = 0; w4 < C / 8; ++w4) {
+      const uint4 qv = *reinterpret_cast<const uint4*>(Qs + qi * RS + w4 * 4);
+      const float2 qa = unpack_bf16x2(qv.x), qb = unpack_bf16x2(qv.y), qc = unpack_bf16x2(qv.z), qd = unpack_bf16x2(qv.w);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 kv = *reinterpret_cast<const uint4*>(KVs + (sub + 8 * j) * RS + w4 * 4);
+        const float2 ka = unpack_bf16x2(kv.x), kb = unpack_bf16x2(kv.y), kc2 = unpack_bf16x2(kv.z), kd = unpack_bf16x2(kv.w);
+        float a = acc[j];
+        a = fmaf(qa.x, ka.x, a); a = fmaf(qa.y, ka.y, a);
+        a = fmaf(qb.x, kb.x, a); a = fmaf(qb.y, kb.y, a);
+        a = fmaf(qc.x, kc2.x, a); a = fmaf(qc.y, kc2.y, a);
+        a = fmaf(qd.x, kd.x, a); a = fmaf(qd.y, kd.y, a);
+        acc[j] = a;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Ss[qi * SW + kc * SA_KCH + sub + 8 * j] = acc[j] * scale;
+  }
+  __syncthreads();
+
+  // ---- softmax over keys (dim=2, :440)
+  for (int r = warp; r < SA_ROWS; r += SA_THREADS / 32) {
+    float* row = Ss + r * SW;
+    float mx = -INFINITY;
+    for (int k = lane; k < T; k += 32) mx = fmaxf(mx, row[k]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < Tpad; k += 32) {
+      const float e = (k < T) ? expf(row[k] - mx) : 0.f;
+      row[k] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int k = lane; k < Tpad; k += 32) row[k] *= inv;
+  }
+
+  // ---- O = P V ; thread -> row qi, dims {i*64 + sub*8 .. +7}
+  float oacc[C / 8];
+#pragma unroll
+  for (int e = 0; e < C / 8; ++e) oacc[e] = 0.f;
+  for (int kc = 0; kc < nchunks; ++kc) {
+    __syncthreads();
+    for (int i = t; i < SA_KCH * V8; i += SA_THREADS) {
+      const int r = i / V8, c8 = i - r * V8;
+      const int key = kc * SA_KCH + r;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (key < T) v = *reinterpret_cast<const uint4*>(base + static_cast<long long>(key) * (3 * C) + 2 * C + c8 * 8);
+      *reinterpret_cast<uint4*>(KVs + r * RS + c8 * 4) = v;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < SA_KCH; ++kk) {
+      const float p = Ss[qi * SW + kc * SA_KCH + kk];
+#pragma unroll
+      for (int i = 0; i < C / 64; ++i) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(KVs + kk * RS + i * 32 + sub * 4);
+        const float2 a = unpack_bf16x2(vv.x), b = unpack_bf16x2(vv.y), c = unpack_bf16x2(vv.z), d = unpack_bf16x2(vv.w);
+        oacc[i * 8 + 0] = fmaf(p, a.x, oacc[i * 8 + 0]);
+        oacc[i * 8 + 1] = fmaf(p, a.y, oacc[i * 8 + 1]);
+        oacc[i * 8 + 2] = fmaf(p, b.x, oacc[i * 8 + 2]);
+        oacc[i * 8 + 3] = fmaf(p, b.y, oacc[i * 8 + 3]);
+        oacc[i * 8 + 4] = fmaf(p, c.x, oacc[i * 8 + 4]);
+        oacc[i * 8 + 5] = fmaf(p, c.y, oacc[i * 8 + 5]);
+        oacc[i * 8 + 6] = fmaf(p, d.x, oacc[i * 8 + 6]);
+        oacc[i * 8 + 7] = fmaf(p, d.y, oacc[i * 8 + 7]);
+      }
+    }
+  }
+  if (q0 + qi < T) {
+    __nv_bfloat16* orow = o + (static_cast<long long>(n) * T + q0 + qi) * C;
+#pragma unroll
+    for (int i = 0; i < C / 64; ++i)
+      *reinterpret_cast<uint4*>(orow + i * 64 + sub * 8) =
+          make_uint4(pack_bf16x2(oacc[i * 8 + 0], oacc[i * 8 + 1]), pack_bf16x2(oacc[i * 8 + 2], oacc[i * 8 + 3]),
+                     pack_bf16x2(oacc[i * 8 + 4], oacc[i * 8 + 5]), pack_bf16x2(oacc[i * 8 + 6], oacc[i * 8 + 7]));
+  }
+}
+
+// ------------------------------------------------------------------ decoder tail: norm_out + swish + conv_out (C -> 1)
+constexpr int CO_TW = 32, CO_TH = 8, CO_THREADS = 128;   // output tile; each thread: 2 vertically adjacent pixels
+
+template <int C>
+__global__ void __launch_bounds__(CO_THREADS)
+norm_swish_conv_out_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ sums,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const float* __restrict__ w, const float* __restrict__ bias, int H, int W,
+                           float* __restrict__ out) {
+  constexpr int PW = C / 2;                 // words per pixel (bf16 pairs)
+  constexpr int IW = CO_TW + 2, IH = CO_TH + 2;
+  extern __shared__ __align__(16) uint32_t co_smem[];
+  uint32_t* tile = co_smem;                 // [IH*IW][PW]
+  float2* wsm = reinterpret_cast<float2*>(tile + IH * IW * PW);  // [9][PW]
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * CO_TW, y0 = blockIdx.y * CO_TH;
+  const int t = threadIdx.x;
+  constexpr int gch = C / GN_GROUPS;
+  const float inv_cnt = 1.0f / (static_cast<float>(H) * static_cast<float>(W) * static_cast<float>(gch));
+
+  for (int i = t; i < 9 * PW; i += CO_THREADS) wsm[i] = make_float2(w[2 * i], w[2 * i + 1]);
+  constexpr int C8 = C / 8;
+  for (int i = t; i < IH * IW * C8; i += CO_THREADS) {
+    const int c8 = i % C8;
+    const int pix = i / C8;
+    const int ly = pix / IW, lx = pix - ly * IW;
+    const int y = y0 + ly - 1, x = x0 + lx - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);       // zero padding applies to the activated tensor
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(h + ((static_cast<long long>(n) * H + y) * W + x) * C) + c8);
+      float m0, r0, m1, r1;
+      gn_mean_rstd(sums, n, (c8 * 8) / gch, inv_cnt, m0, r0);
+      gn_mean_rstd(sums, n, (c8 * 8 + 4) / gch, inv_cnt, m1, r1);
+      v = gn_apply8(raw, m0, r0, m1, r1, gamma, beta, c8 * 8, true);
+    }
+    *reinterpret_cast<uint4*>(tile + pix * PW + c8 * 4) = v;
+  }
+  __syncthreads();
+
+  const int tx = t & 31, ty2 = (t >> 5) * 2;  // output rows ty2, ty2+1
+  const int lane = t & 31;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int c2 = 0; c2 < PW; ++c2) {
+    const int cr = (c2 + lane) & (PW - 1);   // rotate channels across lanes: conflict-free smem banks
+    float2 a[4][3];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) a[r][dx] = unpack_bf16x2(tile[((ty2 + r) * IW + tx + dx) * PW + cr]);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float2 wv = wsm[(dy * 3 + dx) * PW + cr];
+        acc0 = fmaf(a[dy][dx].x, wv.x, acc0);
+        acc0 = fmaf(a[dy][dx].y, wv.y, acc0);
+        acc1 = fmaf(a[dy + 1][dx].x, wv.x, acc1);
+        acc1 = fmaf(a[dy + 1][dx].y, wv.y, acc1);
+      }
+  }
+  const int x = x0 + tx;
+  const float b = bias[0];
+  if (x < W) {
+    const int y = y0 + ty2;
+    if (y < H) out[(static_cast<long long>(n) * H + y) * W + x] = acc0 + b;
+    if (y + 1 < H) out[(static_cast<long long>(n) * H + y + 1) * W + x] = acc1 + b;
+  }
+}
+
+// ------------------------------------------------------------------ encoder head: conv_in 1 -> Cout
+__global__ void __launch_bounds__(256)
+conv_in_1ch_kernel(const float* __restrict__ mel, const float* __restrict__ w, const float* __restrict__ bias, int N,
+                   int H, int W, int Cout, uint4* __restrict__ out) {
+  extern __shared__ float ci_smem[];        // wt[9][Cout] | b[Cout]
+  float* wt = ci_smem;
+  float* bs = wt + 9 * Cout;
+  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
+    const int co = i % Cout, tap = i / Cout;
+    wt[i] = w[co * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias[i];
+  __syncthreads();
+  const int C8 = Cout / 8;
+  const long long total = static_cast<long long>(N) * H * W * C8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    long long r = i / C8;
+    const int x = static_cast<int>(r % W);
+    r /= W;
+    const int y = static_cast<int>(r % H);
+    const long long n = r / H;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bs[c8 * 8 + e];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int yy = y + dy - 1, xx = x + dx - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const float m = __ldg(mel + (n * H + yy) * W + xx);
+        const float* wr = wt + (dy * 3 + dx) * Cout + c8 * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(m, wr[e], acc[e]);
+      }
+    out[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                        pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+}  // namespace
+
+// ====================================================================== host wrappers
+int vqvae_repack_conv_weight(const float* src, int Cout, int Cin, int KH, int KW, __nv_bfloat16* dst, cudaStream_t s) {
+  const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
+  repack_conv_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, Cout, Cin, KH * KW, dst);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_build_gather_table(const float* codebook, const float* wpq, const float* bpq, int K, int Cin, int Cout,
+                             __nv_bfloat16* table, cudaStream_t s) {
+  gather_table_kernel<<<ceil_div(K * Cout, 256), 256, 0, s>>>(codebook, wpq, bpq, K, Cin, Cout, table);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_gather_rows(const long long* idx, const __nv_bfloat16* table, long long n, int C, int K, __nv_bfloat16* out,
+                      int* bad_flag, cudaStream_t s) {
+  MGV_REQUIRE(C % 8 == 0, "gather_rows: C=%d", C);
+  if (n == 0) return MGV_OK;
+  gather_rows_kernel<<<grid_for(n * (C / 8), 256), 256, 0, s>>>(idx, reinterpret_cast<const uint4*>(table), n, C / 8, K,
+                                                                reinterpret_cast<uint4*>(out), bad_flag);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_nchw_f32_to_nhwc_bf16(const float* in, int N, int C, int HW, __nv_bfloat16* out, cudaStream_t s) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  if (total == 0) return MGV_OK;
+  nchw_to_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, N, C, HW, out);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_nhwc_f32_to_nchw_f32(const float* in, int N, int C, int HW, float* out, cudaStream_t s) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  if (total == 0) return MGV_OK;
+  nhwc_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, N, C, HW, out);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_gn_stats(const __nv_bfloat16* x, int N, int HW, int C, float* sums, cudaStream_t s) {
+  MGV_REQUIRE(C % GN_GROUPS == 0 && (C == 128 || C == 256 || C == 512), "gn_stats: C=%d unsupported", C);
+  if (N == 0) return MGV_OK;
+  const long long items = static_cast<long long>(HW) * (C / 8);
+  int chunks = static_cast<int>((items + 256 * 8 - 1) / (256 * 8));
+  const int cap = (num_sms() * 8 + N - 1) / N;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  gn_stats_kernel<<<dim3(chunks, N), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), HW, C, sums);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_gn_apply(const __nv_bfloat16* x, const float* sums, const float* gamma, const float* beta, int N, int HW, int C,
+                   int do_swish, __nv_bfloat16* y, cudaStream_t s) {
+  MGV_REQUIRE(C == 128 || C == 256 || C == 512, "gn_apply: C=%d unsupported", C);
+  const long long total = static_cast<long long>(N) * HW * (C / 8);
+  if (total == 0) return MGV_OK;
+  gn_apply_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), sums, gamma, beta, total, HW, C,
+                                                       do_swish, reinterpret_cast<uint4*>(y));
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_upsample2x(const __nv_bfloat16* x, int N, int H, int W, int C, __nv_bfloat16* y, cudaStream_t s) {
+  MGV_REQUIRE(C % 8 == 0, "upsample: C=%d", C);
+  const long long total = static_cast<long long>(N) * 4 * H * W * (C / 8);
+  if (total == 0) return MGV_OK;
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), N, H, W, C / 8,
+                                                         reinterpret_cast<uint4*>(y));
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_spatial_attention(const __nv_bfloat16* qkv, int N, int T, int C, __nv_bfloat16* o, cudaStream_t s) {
+  MGV_REQUIRE(C == 512, "spatial_attention: C=%d unsupported (the reference attends only at the 512-channel level)", C);
+  MGV_REQUIRE(T >= 1 && T <= 1024, "spatial_attention: T=%d", T);
+  if (N == 0) return MGV_OK;
+  constexpr int RS = 512 / 2 + 4;
+  const int Tpad = ceil_div(T, SA_KCH) * SA_KCH;
+  const size_t smem = (static_cast<size_t>(SA_ROWS) * RS + SA_KCH * RS) * 4 + static_cast<size_t>(SA_ROWS) * (Tpad + 1) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(spatial_attn_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  MGV_REQUIRE(smem <= 200 * 1024, "spatial_attention: T=%d needs too much shared memory", T);
+  spatial_attn_kernel<512><<<dim3(ceil_div(T, SA_ROWS), N), SA_THREADS, smem, s>>>(qkv, T, o);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_norm_swish_conv_out(const __nv_bfloat16* h, const float* sums, const float* gamma, const float* beta,
+                              const float* w, const float* bias, int N, int H, int W, int C, float* out,
+                              cudaStream_t s) {
+  MGV_REQUIRE(C == 128, "conv_out: C=%d unsupported", C);
+  if (N == 0) return MGV_OK;
+  const size_t smem = static_cast<size_t>((CO_TH + 2) * (CO_TW + 2)) * (C / 2) * 4 + 9 * (C / 2) * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(norm_swish_conv_out_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(W, CO_TW), ceil_div(H, CO_TH), N);
+  norm_swish_conv_out_kernel<128><<<grid, CO_THREADS, smem, s>>>(h, sums, gamma, beta, w, bias, H, W, out);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_conv_in_1ch(const float* mel, const float* w, const float* bias, int N, int H, int W, int Cout,
+                      __nv_bfloat16* out, cudaStream_t s) {
+  MGV_REQUIRE(Cout % 8 == 0 && Cout <= 512, "conv_in: Cout=%d", Cout);
+  const long long total = static_cast<long long>(N) * H * W * (Cout / 8);
+  if (total == 0) return MGV_OK;
+  const size_t smem = static_cast<size_t>(10) * Cout * 4;
+  conv_in_1ch_kernel<<<grid_for(total, 256), 256, smem, s>>>(mel, w, bias, N, H, W, Cout, reinterpret_cast<uint4*>(out));
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+}  // namespace mgv

@@ -1,0 +1,157 @@
+"""Drop-in for the reference's feature_extraction/extract_codes.py (mel -> VQ code indices).
+
+Same CLI flags (-i -m -emb_dim -n_e -crop), same `Crop` / `get_codes(...)` signatures, same
+on-disk result: `<dir>/codes_10s/<stem>_code.npy`, int64 (5, 53); files whose output already
+exists are skipped; a file that fails is reported as "is damaged" and the walk continues
+(reference :31-60).  Internally the walk is BATCHED (`get_codes_batch`): crops are stacked
+into one (B,1,80,848) tensor, encoded and quantised by libmgv in one pass per batch, and the
+clips of a batch may be sharded over ranks (one process per GPU, no collective).
+"""
+import argparse
+import os
+import sys
+from glob import glob
+
+import numpy as np
+import torch
+
+from ..vqvae.big_model_attn_gan import LitVQVAE
+
+
+class Crop(object):
+    """Centre (or random) crop to `cropped_shape` = [mel_num, spec_len] (reference :13-29, which
+    delegates to albumentations.CenterCrop / RandomCrop: (H - h)//2, (W - w)//2 offsets)."""
+
+    def __init__(self, cropped_shape=None, random_crop=False):
+        self.cropped_shape = cropped_shape
+        self.random_crop = random_crop
+
+    def __call__(self, item):
+        if self.cropped_shape is None:
+            return item
+        h, w = int(self.cropped_shape[0]), int(self.cropped_shape[1])
+        H, W = item.shape[:2]
+        if H < h or W < w:
+            raise ValueError("Requested crop size (%d, %d) is larger than the image size (%d, %d)" % (h, w, H, W))
+        if self.random_crop:
+            y0 = np.random.randint(0, H - h + 1)
+            x0 = np.random.randint(0, W - w + 1)
+        else:
+            y0, x0 = (H - h) // 2, (W - w) // 2
+        return item[y0:y0 + h, x0:x0 + w]
+
+
+def _out_path(mel_path, folder_name):
+    save_dir = os.path.dirname(os.path.dirname(mel_path))
+    audio_name = os.path.basename(mel_path).split('.')[0]
+    return os.path.join(save_dir + "/" + folder_name, audio_name + '_code.npy')
+
+
+def _load_mel(mel_path, transforms):
+    mel = np.load(mel_path).astype(np.float32)
+    mel = transforms(mel)
+    return 2 * mel - 1                                   # reference :43
+
+
+@torch.no_grad()
+def encode_batch(mels, device, model):
+    """(B,80,848) float32 numpy in [-1,1] -> (B,5,53) int64 numpy codes."""
+    x = torch.from_numpy(np.ascontiguousarray(mels)).unsqueeze(1).to(device, non_blocking=True)
+    y = model.encode(x)
+    idx = model._vq_vae.encoding_indices(y)              # == info[2] of model._vq_vae(y)
+    return idx.reshape(x.shape[0], y.shape[2], y.shape[3]).cpu().numpy()
+
+
+def get_codes(mel_path, device, spec_crop_len, model, transforms, folder_name='codes_10s'):
+    """Single-file entry point with the reference's signature and semantics (:31-60)."""
+    out = _out_path(mel_path, folder_name)
+    if not os.path.isfile(out):
+        try:
+            print("\rworking on", mel_path, end="", flush=True)
+            mel = _load_mel(mel_path, transforms)
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            codes = encode_batch(mel[None], device, model)[0]
+            np.save(out, codes)
+        except Exception:
+            print(mel_path, "is damaged")
+    else:
+        print("\rfile exists:", mel_path, end="", flush=True)
+
+
+def get_codes_batch(mel_paths, device, spec_crop_len, model, transforms, folder_name='codes_10s', batch_size=64):
+    """Batched walk: same per-file results as calling get_codes on each path."""
+    todo = [p for p in mel_paths if not os.path.isfile(_out_path(p, folder_name))]
+    done = 0
+    for i in range(0, len(todo), batch_size):
+        chunk, mels = [], []
+        for p in todo[i:i + batch_size]:
+            try:
+                mels.append(_load_mel(p, transforms))
+                chunk.append(p)
+            except Exception:
+                print(p, "is damaged")
+        if not chunk:
+            continue
+        try:
+            codes = encode_batch(np.stack(mels), device, model)
+        except Exception:
+            for p in chunk:
+                print(p, "is damaged")
+            continue
+        for p, c in zip(chunk, codes):
+            out = _out_path(p, folder_name)
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            np.save(out, c)
+            done += 1
+    return done
+
+
+def shard(paths, rank, world_size):
+    """Contiguous split of the sorted file list by rank (no collective: every rank writes its own files)."""
+    n = len(paths)
+    lo = (n * rank) // world_size
+    hi = (n * (rank + 1)) // world_size
+    return paths[lo:hi]
+
+
+def main(argv=None):
+    paser = argparse.ArgumentParser()
+    paser.add_argument("-i", "--input_dir", default="data/vas/features")
+    paser.add_argument("-m", "--model_dir", default="lightning_logs/2021-06-06T19-42-53_vas_codebook.pt")
+    paser.add_argument("-emb_dim", "--embedding_dim", default=256)
+    paser.add_argument("-n_e", "--num_embeddings", type=int, default=128)
+    paser.add_argument("-crop", "--spec_crop_len", default=848)
+    paser.add_argument("--batch_size", type=int, default=64)
+    args = paser.parse_args(argv)
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("extract_codes: no CUDA device; the B200 path has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    spec_crop_len = int(args.spec_crop_len)
+    input_dir = "../" + args.input_dir            # the reference runs from feature_extraction/ (:79-80)
+    model_dir = "../" + args.model_dir
+    model = LitVQVAE(args.num_embeddings, int(args.embedding_dim))
+    model.load_state_dict(torch.load(model_dir))
+    model.eval().to(device)
+    transforms = Crop([80, spec_crop_len], False)
+
+    folders = sorted(os.listdir(input_dir))
+    if "vggsound" in input_dir:
+        print("In VGGSound")
+        mel_dirs = [input_dir + "/" + f for f in folders if f == "melspec_10s_22050hz"]
+    elif "vas" in input_dir:
+        print("In VAS")
+        mel_dirs = [input_dir + "/" + f + "/" + "melspec_10s_22050hz" for f in folders]
+    else:
+        mel_dirs = []
+    for mel_dir in mel_dirs:
+        mel_paths = sorted(glob(os.path.join(mel_dir, "*.npy")))
+        get_codes_batch(shard(mel_paths, rank, world), device, spec_crop_len, model, transforms, batch_size=args.batch_size)
+
+
+if __name__ == '__main__':
+    main()

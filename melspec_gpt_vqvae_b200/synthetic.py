@@ -115,7 +115,8 @@ def vqvae_param_shapes(num_embeddings=128, embedding_dim=256, encoder=True, deco
             for b in range(nrb):
                 _resblock(s, "%s.down.%d.block.%d" % (e, lvl, b), block_in, block_out)
                 block_in = block_out
-                if lvl == nres - 1:
+            if lvl == nres - 1:   # module order: down.block.* precede down.attn.*
+                for b in range(nrb):
                     _attnblock(s, "%s.down.%d.attn.%d" % (e, lvl, b), block_in)
             if lvl != nres - 1:
                 s["%s.down.%d.downsample.conv.weight" % (e, lvl)] = (block_in, block_in, 3, 3)
@@ -143,7 +144,8 @@ def vqvae_param_shapes(num_embeddings=128, embedding_dim=256, encoder=True, deco
             for b in range(nrb + 1):
                 _resblock(keys, "%s.up.%d.block.%d" % (d, lvl, b), block_in, block_out)
                 block_in = block_out
-                if lvl == nres - 1:
+            if lvl == nres - 1:
+                for b in range(nrb + 1):
                     _attnblock(keys, "%s.up.%d.attn.%d" % (d, lvl, b), block_in)
             if lvl != 0:
                 keys["%s.up.%d.upsample.conv.weight" % (d, lvl)] = (block_in, block_in, 3, 3)

@@ -143,7 +143,15 @@ def main():
     m.load_state_dict(sd)
     x, c = gpt_inputs(2, 265, 128, 8, seed=0)
     logits, _, att = m(x[:, :-1], c)
-    np.savez_compressed(os.path.join(out, "gpt_vas.npz"), logits=logits.numpy(), att_rows=att[:, :, ::33].numpy())
+    # yardstick: the reference's own error when it computes in bf16 (torch.autocast) instead of fp32
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        logits_bf, _, att_bf = m(x[:, :-1], c)
+    eb = (logits_bf.float() - logits).abs()
+    ea = (att_bf.float() - att).abs()
+    np.savez_compressed(os.path.join(out, "gpt_vas.npz"), logits=logits.numpy(), att_rows=att[:, :, ::33].numpy(),
+                        autocast_logit_err_max=eb.max().numpy(), autocast_logit_err_rms=eb.pow(2).mean().sqrt().numpy(),
+                        autocast_att_err_max=ea.max().numpy())
+    print("autocast yardstick: logits max %.4f rms %.4f att max %.5f" % (eb.max(), eb.pow(2).mean().sqrt(), ea.max()))
     print("gpt vas", logits.shape, float(logits.std()))
     del m, sd
 
@@ -159,7 +167,15 @@ def main():
     mel = m.decode(quant)
     melin = torch.rand(1, 1, 80, 848, generator=g) * 2 - 1
     z = m.encode(melin)
-    np.savez_compressed(os.path.join(out, "vqvae.npz"), mel=mel.numpy(), z=z.numpy())
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        mel_bf = m.decode(quant)
+        z_bf = m.encode(melin)
+    em = (mel_bf.float() - mel).abs()
+    ez = (z_bf.float() - z).abs()
+    print("autocast yardstick: mel max %.4f rms %.4f ; z max %.4f rms %.4f" % (em.max(), em.pow(2).mean().sqrt(), ez.max(), ez.pow(2).mean().sqrt()))
+    np.savez_compressed(os.path.join(out, "vqvae.npz"), mel=mel.numpy(), z=z.numpy(),
+                        autocast_mel_err_max=em.max().numpy(), autocast_mel_err_rms=em.pow(2).mean().sqrt().numpy(),
+                        autocast_z_err_max=ez.max().numpy(), autocast_z_err_rms=ez.pow(2).mean().sqrt().numpy())
     print("vqvae mel", mel.shape, float(mel.std()), "z", z.shape, float(z.std()))
 
 

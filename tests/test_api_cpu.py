@@ -1,0 +1,123 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mgv.h declares (no compute calls),
+host-side logic (state_dict layout, Crop, sharding, error behaviour without a device)."""
+import argparse
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from melspec_gpt_vqvae_b200 import _lib, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mgv.h")).read()
+    declared = set(re.findall(r"\b(mgv_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libmgv.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.mgv_version() == 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device error path")
+def test_no_cpu_fallback_without_device():
+    lib = _lib.load()
+    assert lib.mgv_device_check() == 3          # MGV_ERR_DEVICE
+    assert "no CPU fallback" in _lib.last_error()
+    from melspec_gpt_vqvae_b200.vqvae.big_model_attn_gan import VectorQuantizer
+    vq = VectorQuantizer(128, 256, 0.25)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq(torch.zeros(1, 256, 5, 53))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq.get_codebook_entry(torch.zeros(4, dtype=torch.long), None)
+
+
+def test_gpt_state_dict_layout_matches_reference_enumeration():
+    from melspec_gpt_vqvae_b200.transformer.minGPT import GPTClass
+    cfg = dict(synthetic.GPT_VAS, n_layer=2)
+    m = GPTClass(argparse.Namespace(embd_pdrop=0.5, resid_pdrop=0.5, attn_pdrop=0.5, **cfg))
+    sd = m.state_dict()
+    want = synthetic.gpt_param_shapes(cfg)
+    keys = [k for k in sd if not k.endswith("attn.mask")]
+    assert keys == list(want), "key order / names differ"
+    for k, shape in want.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert tuple(sd["blocks.0.attn.mask"].shape) == (1, 1, 266, 266)      # persistent buffer, like the reference
+    # full VAS config: 414 keys / 302 854 144 parameters
+    full = synthetic.gpt_param_shapes(synthetic.GPT_VAS)
+    assert len(full) + 24 == 414
+    assert sum(int(np.prod(s)) for s in full.values()) == 302854144
+    # init distributions (reference _init_weights): LayerNorm (1,0), Linear bias 0, pos_emb 0
+    assert float(sd["ln_f.weight"].min()) == 1.0 and float(sd["blocks.0.mlp.0.bias"].abs().max()) == 0.0
+    assert float(sd["pos_emb"].abs().max()) == 0.0
+    assert abs(float(sd["tok_emb.weight"].std()) - 0.02) < 2e-3
+
+
+def test_vqvae_state_dict_layout():
+    from melspec_gpt_vqvae_b200.vqvae.big_model_attn_gan import LitVQVAE
+    m = LitVQVAE(128, 256)
+    sd = m.state_dict()
+    want = synthetic.vqvae_param_shapes(128, 256)
+    hot = [k for k in sd if not k.startswith("discriminator.")]
+    assert hot == list(want)
+    for k, shape in want.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    n = lambda p: sum(v.numel() for k, v in sd.items() if k.startswith(p) and "num_batches" not in k and "running" not in k)
+    assert n("_encoder.") == 29295872 and n("_decoder.") == 42447489          # SURVEY appendix A [probed]
+    assert n("discriminator.") == 2763585 + 0 or n("discriminator.") > 0
+    assert sd["discriminator.main.0.weight"].shape == (64, 1, 4, 4) and "discriminator.main.9.running_var" in sd
+    # codebook init U(+-1/K)
+    assert float(sd["_vq_vae._embedding.weight"].abs().max()) <= 1 / 128
+
+
+def test_reference_state_dict_keys_if_available():
+    import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    vq, gpt = ref_shim.import_reference()
+    ref = vq.LitVQVAE(128, 256).state_dict()
+    from melspec_gpt_vqvae_b200.vqvae.big_model_attn_gan import LitVQVAE
+    ours = LitVQVAE(128, 256).state_dict()
+    assert list(ref.keys()) == list(ours.keys())
+    assert all(ref[k].shape == ours[k].shape for k in ref)
+    cfg = dict(synthetic.GPT_VAS, n_layer=1)
+    a = argparse.Namespace(embd_pdrop=0.5, resid_pdrop=0.5, attn_pdrop=0.5, **cfg)
+    from melspec_gpt_vqvae_b200.transformer.minGPT import GPTClass
+    r, o = gpt.GPTClass(a).state_dict(), GPTClass(a).state_dict()
+    assert list(r.keys()) == list(o.keys()) and all(r[k].shape == o[k].shape for k in r)
+
+
+def test_crop_and_shard_host_logic():
+    from melspec_gpt_vqvae_b200.feature_extraction import extract_codes as ec
+    a = np.arange(80 * 860, dtype=np.float32).reshape(80, 860)
+    assert np.array_equal(ec.Crop([80, 848], False)(a), a[:, 6:854])
+    assert ec.Crop(None)(a) is a
+    with pytest.raises(ValueError):
+        ec.Crop([80, 848], False)(a[:, :100])
+    paths = ["f%03d" % i for i in range(10)]
+    parts = [ec.shard(paths, r, 4) for r in range(4)]
+    assert sum(parts, []) == paths and max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert ec.shard([], 0, 2) == []
+    assert ec._out_path("/x/features/dog/melspec_10s_22050hz/a_mel.npy", "codes_10s") == "/x/features/dog/codes_10s/a_mel_code.npy"
+
+
+def test_code_reader_host_logic():
+    from melspec_gpt_vqvae_b200.transformer.minGPT import Lit_minGPT
+    lit = Lit_minGPT.__new__(Lit_minGPT)
+    torch.nn.Module.__init__(lit)
+    lit.forward_shuffle_idx, lit.backward_shuffle_idx = Lit_minGPT.make_idx(lit, 5, 53)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "code_reader.npz"))
+    assert np.array_equal(lit.forward_shuffle_idx.numpy(), g["fwd"]) and np.array_equal(lit.backward_shuffle_idx.numpy(), g["bwd"])
+    x = torch.arange(2 * 265).reshape(2, 265)
+    assert torch.equal(lit.code_reader(lit.code_reader(x), reverse=True), x)
+    # get_x: codes (B,5,53) -> (B,265) time-major == code_reader(row-major flatten)
+    lit.args = argparse.Namespace(device="cpu")
+    codes = torch.arange(2 * 265).reshape(2, 5, 53)
+    assert torch.equal(lit.get_x({"codes": codes}), lit.code_reader(codes.reshape(2, -1)))
+    lg = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "topk.npz"))["logits"])
+    assert torch.equal(lit.top_k_logits(lg, 100), torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "topk.npz"))["out100"]))

@@ -1,0 +1,86 @@
+"""GPU: the tcgen05 GEMM / implicit-GEMM conv kernel against the SIMT fp32 reference kernel of the same
+contract (exactly the same bf16 inputs, fp32 accumulation -> tight tolerance) and against torch."""
+import ctypes
+
+import pytest
+import torch
+
+from melspec_gpt_vqvae_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+S0 = ctypes.c_void_p(0)
+
+
+def run_gemm(impl, A, B, epi, bias, out, resid, bn, split):
+    M, K = A.shape
+    N = B.shape[0]
+    _lib.check(_lib.load().mgv_test_gemm(impl, _lib.ptr(A), _lib.ptr(B), M, N, K, epi, _lib.ptr(bias), _lib.ptr(out),
+                                         _lib.ptr(resid), bn, split, S0))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K,bn,split,epi", [
+    (128, 128, 64, 128, 1, 2), (1, 32, 64, 32, 1, 2), (64, 3072, 1024, 128, 8, 4), (64, 1024, 4096, 64, 8, 4),
+    (64, 4096, 1024, 128, 4, 4), (64, 128, 1024, 128, 1, 2), (300, 256, 512, 256, 1, 2), (1000, 384, 1024, 128, 1, 0),
+    (777, 4096, 1024, 128, 1, 1), (1000, 1024, 4096, 64, 1, 3), (530, 1472, 1472, 32, 1, 5), (16960, 1024, 1024, 128, 1, 3),
+])
+def test_gemm_vs_simt_reference(M, N, K, bn, split, epi):
+    torch.manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    bf16_out = epi in (0, 1, 5)
+    init = torch.randn(M, N, device="cuda")
+    outs = []
+    for impl in (0, 1):
+        out = (torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if bf16_out else init.clone())
+        resid = None
+        if epi == 3:
+            resid = out
+        if epi == 5:
+            resid = init.bfloat16()
+        run_gemm(impl, A, B, epi, bias, out, resid, bn, split if impl == 0 else 1)
+        outs.append(out.float())
+    ref = A.float() @ B.float().t() + bias
+    scale = ref.abs().max().item()
+    err = (outs[0] - outs[1]).abs().max().item()
+    tol = (1.0 / 128) * scale if bf16_out else 2e-5 * scale * (K ** 0.5)
+    assert err <= tol, "tcgen05 vs SIMT: max err %.3e (tol %.3e)" % (err, tol)
+    if epi == 2:
+        assert (outs[0] - ref).abs().max().item() <= 1e-3 * scale
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout,stride,resid", [
+    (2, 5, 53, 256, 512, 1, False), (2, 10, 106, 512, 512, 1, True), (1, 40, 424, 128, 128, 1, False),
+    (1, 80, 848, 128, 128, 1, True), (2, 80, 848, 128, 128, 2, False), (2, 10, 106, 256, 256, 2, False),
+    (3, 20, 212, 256, 128, 1, False),
+])
+def test_conv3x3_vs_torch(n, H, W, Cin, Cout, stride, resid):
+    torch.manual_seed(H * W + Cin)
+    x = (torch.randn(n, H, W, Cin, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(Cout, device="cuda")
+    xn, wn = x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2)
+    if stride == 1:
+        ref = torch.nn.functional.conv2d(xn, wn, bias, padding=1)
+    else:   # Downsample: pad (0,1,0,1) then stride 2 (reference big_model_attn_gan.py:151-159)
+        ref = torch.nn.functional.conv2d(torch.nn.functional.pad(xn, (0, 1, 0, 1)), wn, bias, stride=2)
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    r = None
+    if resid:
+        r = torch.randn_like(ref).bfloat16()
+        ref = ref + r.float()
+    out = torch.zeros(ref.shape, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.load().mgv_test_conv3x3(0, _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), n, H, W, Cin, Cout, stride,
+                                            _lib.ptr(out), _lib.ptr(r), S0))
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (out.float() - ref).abs().max().item() <= (1.0 / 64) * scale
+
+
+def test_gemm_rejects_bad_shapes():
+    A = torch.zeros(4, 60, device="cuda", dtype=torch.bfloat16)
+    B = torch.zeros(32, 60, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(4, 32, device="cuda")
+    rc = _lib.load().mgv_test_gemm(0, _lib.ptr(A), _lib.ptr(B), 4, 32, 60, 2, None, _lib.ptr(out), None, 32, 1, S0)
+    assert rc != 0 and "multiple of 64" in _lib.last_error()
