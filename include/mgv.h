@@ -156,6 +156,11 @@ int64_t mgv_vqvae_last_launches(const mgv_vqvae_t* v);
 int mgv_test_gemm(int impl, const void* A, const void* B, int M, int N, int K, int epi, const float* bias,
                   void* out, const void* resid, int bn, int split_k, mgv_stream_t stream);
 
+/* Swap-AB form used by the decode step: W bf16 (M = out features, K) is the 128-row MMA operand, X bf16
+ * (N = batch rows, K) the MMA N dimension; out[n * M + m] (+ bias[m]).  N need not be a multiple of 32. */
+int mgv_test_gemm_swapab(int impl, const void* W, const void* X, int M, int N, int K, int epi, const float* bias,
+                         void* out, const void* resid, int bn, int split_k, mgv_stream_t stream);
+
 /* 3x3 convolution (stride 1 pad 1, or stride 2 with the reference's (0,1,0,1) padding) over
  * NHWC bf16 input through the implicit-GEMM path (impl 0) or the SIMT reference (impl 1).
  * w: bf16 (Cout, 3, 3, Cin). */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "mgv_vqvae_encode": (I, [VP, VP, I, VP, VP]),
     "mgv_vqvae_last_launches": (I64, [VP]),
     "mgv_test_gemm": (I, [I, VP, VP, I, I, I, I, VP, VP, VP, I, I, VP]),
+    "mgv_test_gemm_swapab": (I, [I, VP, VP, I, I, I, I, VP, VP, VP, I, I, VP]),
     "mgv_test_conv3x3": (I, [I, VP, VP, VP, I, I, I, I, I, I, VP, VP, VP]),
 }
 

@@ -38,7 +38,10 @@ struct KParams {
   int H, W, Cin, wb, hb, tiles_x, tiles_y, stride, pad;
   float* gn_sum;
   int gn_group_ch;
-  int evict_first_b;
+  int evict_first_w;   // L2 evict-first hint on the weight operand
+  int transpose_out;   // swap-AB: weights are the A operand, output written transposed
+  int* split_counters; // split-K finisher ticket counters (per feature tile) or null
+  void* finish_out;    // bf16 gelu(acc) written by the last split CTA
 };
 
 template <int BN>
@@ -54,6 +57,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bins = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][64] GroupNorm partial sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -78,6 +82,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     y0 = ty * p.hb;
   }
 
+  if (threadIdx.x >= 64) {   // 128 epilogue threads clear their warp's 64 bins
+    s_bins[threadIdx.x - 64] = 0.f;
+    s_bins[threadIdx.x + 64] = 0.f;
+  }
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -96,12 +104,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // let the dependent grid start its prologue (and prefetch its weights) now; its griddepcontrol.wait
+  // still blocks until this grid has completed and flushed
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      const uint64_t hint_b = p.evict_first_b ? kEvictFirst : kEvictNormal;
-      const uint64_t hint_a = kEvictNormal;
+      const uint64_t hint_w = p.evict_first_w ? kEvictFirst : kEvictNormal;
+      const uint64_t hint_b = p.transpose_out ? kEvictNormal : hint_w;
+      const uint64_t hint_a = p.transpose_out ? hint_w : kEvictNormal;
       const int cblocks = (p.a_mode == A_PLAIN) ? 1 : (p.Cin / BK);
       auto load_a = [&](int kb, int s) {
         uint8_t* dst = smem + s * STAGE_BYTES;
@@ -125,10 +137,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int pre = nkb < stages ? nkb : stages;
       for (int kb = 0; kb < pre; ++kb) {  // weights first: they do not depend on the upstream grid
         mbar_arrive_expect_tx(&full_bar[kb], STAGE_BYTES);
-        load_b(kb, kb);
+        if (p.transpose_out) load_a(kb, kb); else load_b(kb, kb);
       }
       pdl_wait();
-      for (int kb = 0; kb < pre; ++kb) load_a(kb, kb);
+      for (int kb = 0; kb < pre; ++kb) {
+        if (p.transpose_out) load_b(kb, kb); else load_a(kb, kb);
+      }
       for (int kb = pre; kb < nkb; ++kb) {
         const int s = kb % stages;
         const uint32_t ph = (kb / stages) & 1;
@@ -179,6 +193,89 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const bool add_bias = p.bias != nullptr && (p.epi != EPI_F32_ATOMIC || blockIdx.z == 0);
+    if (p.transpose_out) {
+      // swap-AB: this thread owns output feature `feat`; accumulator columns are batch rows.  For a fixed
+      // batch row the 32 lanes of a warp touch 32 consecutive features: coalesced stores / reductions.
+      const int feat = m0 + r_local;
+      const bool feat_ok = feat < p.M;
+      const float bval = (add_bias && feat_ok) ? __ldg(p.bias + feat) : 0.f;
+      // NOTE: this kernel runs for a few microseconds per launch in the decode loop, so the code executed
+      // here is kept COMPACT (instruction fetch of a bloated, fully unrolled epilogue costs more than the math).
+      if (p.epi == EPI_F32_ATOMIC) {
+        float* outf = static_cast<float*>(p.out) + feat;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < p.N && feat_ok)
+              atomicAdd(outf + static_cast<long long>(col0 + j) * p.ldo, __uint_as_float(r[j]) + bval);
+          }
+        }
+      } else {
+        const int ncols = (p.N - n0 < BN) ? p.N - n0 : BN;
+#pragma unroll 1
+        for (int j = 0; j < ncols; ++j) {   // one accumulator column (= batch row) at a time
+          const uint32_t raw = tmem_ld_32x32_x1(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + j);
+          tmem_ld_wait();
+          if (feat_ok) {
+            const float v = __uint_as_float(raw) + bval;
+            const long long o = static_cast<long long>(n0 + j) * p.ldo + feat;
+            switch (p.epi) {
+              case EPI_F32: static_cast<float*>(p.out)[o] = v; break;
+              case EPI_F32_RESID: static_cast<float*>(p.out)[o] = static_cast<const float*>(p.resid)[o] + v; break;
+              case EPI_BF16_GELU: static_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(gelu_erf(v)); break;
+              case EPI_BF16_RESID:
+                static_cast<__nv_bfloat16*>(p.out)[o] =
+                    __float2bfloat16(v + __bfloat162float(static_cast<const __nv_bfloat16*>(p.resid)[o]));
+                break;
+              default: static_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(v); break;
+            }
+          }
+        }
+      }
+      if (p.split_counters != nullptr) {
+        // "last block" pattern: publish our reductions, take a ticket; the CTA that draws the last ticket of
+        // this feature tile sees every split's contribution and finishes the tile (GELU -> bf16, clear acc).
+        uint32_t* s_ticket = tmem_slot + 1;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int tile = blockIdx.x * gridDim.y + blockIdx.y;
+          *s_ticket = static_cast<uint32_t>(atomicAdd(p.split_counters + tile, 1));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*s_ticket == gridDim.z - 1) {
+          __threadfence();
+          if (feat_ok) {
+            float* acc32 = static_cast<float*>(p.out);
+            __nv_bfloat16* fo = static_cast<__nv_bfloat16*>(p.finish_out);
+            const int bend = (n0 + BN < p.N) ? n0 + BN : p.N;
+            // 8 independent L2 loads in flight per thread (lanes = consecutive features: coalesced rows)
+#pragma unroll 1
+            for (int b0 = n0; b0 < bend; b0 += 8) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                v[i] = (b0 + i < bend) ? __ldcg(acc32 + static_cast<long long>(b0 + i) * p.ldo + feat) : 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (b0 + i < bend) {
+                  const long long o = static_cast<long long>(b0 + i) * p.ldo + feat;
+                  fo[o] = __float2bfloat16(gelu_erf(v[i]));
+                  acc32[o] = 0.f;
+                }
+              }
+            }
+          }
+          if (threadIdx.x == 64) p.split_counters[blockIdx.x * gridDim.y + blockIdx.y] = 0;
+        }
+      }
+    } else
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int col0 = n0 + c * 32;
@@ -229,25 +326,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (p.gn_sum != nullptr) {
           // GroupNorm statistics of the stored (bf16-rounded) values; a tile never spans images.
+          // Per lane: (sum, sumsq) of each channel group of this 32-column chunk -> 2*(32/gch) <= 16 values;
+          // a transposing butterfly (16 shuffles) leaves one fully reduced value per lane pair, which goes to
+          // the per-CTA shared-memory bins (flushed once per CTA after the chunk loop).
           const int gch = p.gn_group_ch;          // 4, 8 or 16 channels per group
-          const int ngroups_chunk = 32 / gch;
-          float* dst = p.gn_sum + (static_cast<long long>(img) * (p.N / gch) + col0 / gch) * 2;
-          for (int g = 0; g < ngroups_chunk; ++g) {
-            float s = 0.f, ss = 0.f;
-            if (row_ok) {
-              for (int e = 0; e < gch; e += 2) {
-                const float2 f = unpack_bf16x2(pk[(g * gch + e) >> 1]);
-                s += f.x + f.y;
-                ss += f.x * f.x + f.y * f.y;
+          float st[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) st[i] = 0.f;
+          if (row_ok) {
+            float sq[16], sm[16];                 // per channel pair
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 f = unpack_bf16x2(pk[j]);
+              sm[j] = f.x + f.y;
+              sq[j] = f.x * f.x + f.y * f.y;
+            }
+            if (gch == 4) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                st[2 * g] = sm[2 * g] + sm[2 * g + 1];
+                st[2 * g + 1] = sq[2 * g] + sq[2 * g + 1];
+              }
+            } else if (gch == 8) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                st[2 * g] = (sm[4 * g] + sm[4 * g + 1]) + (sm[4 * g + 2] + sm[4 * g + 3]);
+                st[2 * g + 1] = (sq[4 * g] + sq[4 * g + 1]) + (sq[4 * g + 2] + sq[4 * g + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  a += sm[8 * g + e];
+                  b += sq[8 * g + e];
+                }
+                st[2 * g] = a;
+                st[2 * g + 1] = b;
               }
             }
-            s = warp_sum(s);
-            ss = warp_sum(ss);
-            if (lane == 0) {
-              atomicAdd(dst + 2 * g, s);
-              atomicAdd(dst + 2 * g + 1, ss);
+          }
+          // butterfly: after the steps with offsets 16, 8, 4, 2 lane l holds value index (l >> 1) & 15
+#pragma unroll
+          for (int step = 0; step < 4; ++step) {
+            const int off = 16 >> step, n = 8 >> step;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              const float send = upper ? st[i] : st[i + n];
+              const float keep = upper ? st[i + n] : st[i];
+              st[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
             }
           }
+          st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
+          const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          const int nvals = 2 * (32 / gch);
+          // each warp owns its bins (one writer per bin): plain, deterministic accumulation
+          if ((lane & 1) == 0 && vidx < nvals) s_bins[quarter * 64 + c * nvals + vidx] += st[0];
         }
       } else if (row_ok) {
         float* o = static_cast<float*>(p.out) + out_row + col0;
@@ -273,9 +409,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if (p.gn_sum != nullptr) {
+      // one plain store per CTA and bin into this tile's slot (deterministic; folded by vqvae_gn_finalize)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int nbins = (BN / p.gn_group_ch) * 2;
+      const int b = threadIdx.x - 64;
+      const int groups_total = p.N / p.gn_group_ch;
+      const int g0 = n0 / p.gn_group_ch;
+      if (b >= 0 && b < nbins && g0 + (b >> 1) < groups_total)
+        p.gn_sum[(static_cast<long long>(blockIdx.x) * groups_total + g0 + (b >> 1)) * 2 + (b & 1)] =
+            (s_bins[b] + s_bins[64 + b]) + (s_bins[128 + b] + s_bins[192 + b]);
+    }
   }
 
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -308,8 +454,8 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* __restrict__ A, const __nv_
       for (int c = 0; c < p.Cin; ++c) acc = fmaf(__bfloat162float(a[c]), __bfloat162float(b[c]), acc);
     }
   }
-  if (p.bias) acc += p.bias[n];
-  const long long o = m * p.ldo + n;
+  if (p.bias) acc += p.transpose_out ? p.bias[m] : p.bias[n];
+  const long long o = p.transpose_out ? static_cast<long long>(n) * p.ldo + m : m * p.ldo + n;
   switch (p.epi) {
     case EPI_BF16: static_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(acc); break;
     case EPI_BF16_GELU: static_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(gelu_erf(acc)); break;
@@ -326,7 +472,8 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* __restrict__ A, const __nv_
 int fill_params(const GemmArgs& a, KParams& p) {
   MGV_REQUIRE(a.A && a.B && a.out, "gemm: null operand");
   MGV_REQUIRE(a.K > 0 && a.K % BK == 0, "gemm: K=%d must be a positive multiple of %d", a.K, BK);
-  MGV_REQUIRE(a.N > 0 && a.N % 32 == 0, "gemm: N=%d must be a multiple of 32", a.N);
+  MGV_REQUIRE(a.N > 0 && (a.transpose_out || a.N % 32 == 0), "gemm: N=%d must be a multiple of 32", a.N);
+  MGV_REQUIRE(!a.transpose_out || (a.a_mode == A_PLAIN && a.gn_sum == nullptr), "gemm: transpose_out is a plain-GEMM mode");
   MGV_REQUIRE(a.M > 0, "gemm: M=%d", a.M);
   MGV_REQUIRE(a.split_k >= 1, "gemm: split_k=%d", a.split_k);
   MGV_REQUIRE(a.split_k == 1 || a.epi == EPI_F32_ATOMIC, "gemm: split_k>1 needs EPI_F32_ATOMIC");
@@ -339,9 +486,15 @@ int fill_params(const GemmArgs& a, KParams& p) {
   p.bias = a.bias;
   p.out = a.out;
   p.resid = a.resid;
-  p.ldo = a.ldo ? a.ldo : a.N;
+  p.ldo = a.ldo ? a.ldo : (a.transpose_out ? a.M : a.N);
   p.a_mode = a.a_mode;
-  p.evict_first_b = a.weights_evict_first ? 1 : 0;
+  p.evict_first_w = a.weights_evict_first ? 1 : 0;
+  p.transpose_out = a.transpose_out ? 1 : 0;
+  p.split_counters = a.split_counters;
+  p.finish_out = a.finish_out;
+  if (a.split_counters) {
+    MGV_REQUIRE(a.transpose_out && a.epi == EPI_F32_ATOMIC && a.finish_out, "gemm: split-K finisher needs transpose_out + EPI_F32_ATOMIC");
+  }
   p.gn_sum = a.gn_sum;
   p.gn_group_ch = a.gn_group_ch;
   if (a.gn_sum) {
@@ -379,7 +532,7 @@ int launch_tc(const GemmArgs& a, KParams& p) {
   if (a.max_stages > 0 && a.max_stages < max_stages) max_stages = a.max_stages;
   p.stages = p.kb_per_split < max_stages ? p.kb_per_split : max_stages;
   if (p.stages < 1) p.stages = 1;
-  const size_t smem = static_cast<size_t>(p.stages) * STAGE_BYTES + (2 * p.stages + 1) * 8 + 16 + 1024;
+  const size_t smem = static_cast<size_t>(p.stages) * STAGE_BYTES + (2 * p.stages + 1) * 8 + 16 + 1024 + 1024;
 
   CUtensorMap tmA, tmB;
   if (a.a_mode == A_PLAIN) {

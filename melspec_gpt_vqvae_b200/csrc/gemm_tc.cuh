@@ -46,11 +46,23 @@ struct GemmArgs {
   int n_img = 0, H = 0, W = 0, Hin = 0, Win = 0, Cin = 0, stride = 1, pad = 1;
   // GroupNorm statistics fused into the epilogue (conv): per (image, channel-group of
   // `gn_group_ch` output channels) sum and sum of squares of the bf16-rounded outputs.
-  float* gn_sum = nullptr;  // [n_img, N / gn_group_ch, 2] fp32, pre-zeroed
+  // Every CTA stores (no atomics -> deterministic) its partial sums to
+  // gn_sum[(img * tiles_per_image + tile) * (N / gn_group_ch) * 2 + group * 2 + {0: sum, 1: sumsq}];
+  // vqvae_gn_finalize folds the tiles in a fixed order.
+  float* gn_sum = nullptr;
   int gn_group_ch = 0;
+  // swap-AB (decode): A = weights [M = out features, K], B = activations [N = batch rows, K]; the
+  // accumulator tile is written TRANSPOSED: out[n * ldo + m] (ldo defaults to M), bias is per m.
+  // N need not be a multiple of 32 (TMA zero-fills the missing activation rows).
+  bool transpose_out = false;
+  // split-K finisher (transpose_out + EPI_F32_ATOMIC): the last split CTA of a feature tile (ticket from
+  // split_counters[tile], zero-initialised, self-resetting) reads the reduced tile back, writes
+  // finish_out = bf16(gelu_erf(acc)) and clears the accumulator for its next use.
+  int* split_counters = nullptr;
+  void* finish_out = nullptr;
   // launch
   bool pdl = false;
-  bool weights_evict_first = false;
+  bool weights_evict_first = false;  // L2 evict-first hint on the weight operand (B, or A when transpose_out)
   cudaStream_t stream = nullptr;
 };
 

@@ -41,11 +41,12 @@ struct GptLayer {
   float *bqkv, *bproj, *bfc1, *bfc2;
 };
 
+// split-K factors of the decode-step GEMMs (swap-AB: 128 weight rows per CTA x split-K slices)
 struct DecodeTiles {
-  int qkv_bn = 128, qkv_split = 8;
-  int proj_bn = 64, proj_split = 8;
-  int fc1_bn = 128, fc1_split = 4;
-  int fc2_bn = 64, fc2_split = 8;
+  int qkv_split = 8;    // 24 row tiles x 8  = 192 CTAs
+  int proj_split = 16;  //  8 row tiles x 16 = 128 CTAs
+  int fc1_split = 4;    // 32 row tiles x 4  = 128 CTAs
+  int fc2_split = 16;   //  8 row tiles x 16 = 128 CTAs
 };
 
 struct Gpt {
@@ -67,6 +68,7 @@ struct Gpt {
   float *dx = nullptr, *dqkv32 = nullptr, *dh32 = nullptr;
   __nv_bfloat16 *dln = nullptr, *dy = nullptr, *dh = nullptr, *kv = nullptr;
   int* d_state = nullptr;  // [0]=pos, [1]=done counter, [2]=err flag
+  int* d_counters = nullptr;  // split-K finisher tickets (zero-initialised, self-resetting)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   bool pdl = false;
@@ -178,6 +180,7 @@ int run_layers_prefill(Gpt* g, int B, int T, float* att_out, int att_T, bool wri
     MGV_TRY(gpt_layernorm(g->x, w.ln1_w, w.ln1_b, rows, C, g->ln, nullptr, 0, s, false));
     GemmArgs a;
     a.stream = s;
+    a.max_stages = 3;   // 96 KB of smem -> two CTAs per SM (epilogue of one overlaps the MMAs of the other)
     a.A = g->ln; a.B = w.wqkv; a.M = rows; a.N = 3 * C; a.K = C;
     a.epi = EPI_BF16; a.bias = w.bqkv; a.out = g->qkv; a.bn = pick_bn(a.N);
     MGV_TRY(gemm_bf16_tc(a));
@@ -187,17 +190,20 @@ int run_layers_prefill(Gpt* g, int B, int T, float* att_out, int att_T, bool wri
                                   s));
     a = GemmArgs();
     a.stream = s;
+    a.max_stages = 3;   // 96 KB of smem -> two CTAs per SM (epilogue of one overlaps the MMAs of the other)
     a.A = g->y; a.B = w.wproj; a.M = rows; a.N = C; a.K = C;
     a.epi = EPI_F32_RESID; a.bias = w.bproj; a.out = g->x; a.resid = g->x; a.bn = pick_bn(a.N);
     MGV_TRY(gemm_bf16_tc(a));
     MGV_TRY(gpt_layernorm(g->x, w.ln2_w, w.ln2_b, rows, C, g->ln, nullptr, 0, s, false));
     a = GemmArgs();
     a.stream = s;
+    a.max_stages = 3;   // 96 KB of smem -> two CTAs per SM (epilogue of one overlaps the MMAs of the other)
     a.A = g->ln; a.B = w.wfc1; a.M = rows; a.N = 4 * C; a.K = C;
     a.epi = EPI_BF16_GELU; a.bias = w.bfc1; a.out = g->h; a.bn = pick_bn(a.N);
     MGV_TRY(gemm_bf16_tc(a));
     a = GemmArgs();
     a.stream = s;
+    a.max_stages = 3;   // 96 KB of smem -> two CTAs per SM (epilogue of one overlaps the MMAs of the other)
     a.A = g->h; a.B = w.wfc2; a.M = rows; a.N = C; a.K = 4 * C;
     a.epi = EPI_F32_RESID; a.bias = w.bfc2; a.out = g->x; a.resid = g->x; a.bn = pick_bn(a.N);
     MGV_TRY(gemm_bf16_tc(a));
@@ -252,16 +258,18 @@ int gpt_create(const GptConfig* cfg, Gpt** out) {
   g->loaded.assign(g->n_tensors, 0);
   cudaMalloc(&g->d_state, 4 * sizeof(int));
   cudaMemset(g->d_state, 0, 4 * sizeof(int));
+  cudaMalloc(&g->d_counters, 1024 * sizeof(int));
+  cudaMemset(g->d_counters, 0, 1024 * sizeof(int));
   cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&g->ev_in, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&g->ev_out, cudaEventDisableTiming);
   const char* e = getenv("MGV_PDL");
-  g->pdl = e && atoi(e) != 0;
-  const char* tl = getenv("MGV_DECODE_TILES");
+  g->pdl = e ? atoi(e) != 0 : true;   // programmatic dependent launch between the decode-step kernels
+  const char* tl = getenv("MGV_DECODE_SPLITS");
   if (tl) {
     DecodeTiles t;
-    if (sscanf(tl, "%d,%d,%d,%d,%d,%d,%d,%d", &t.qkv_bn, &t.qkv_split, &t.proj_bn, &t.proj_split, &t.fc1_bn,
-               &t.fc1_split, &t.fc2_bn, &t.fc2_split) == 8)
+    if (sscanf(tl, "%d,%d,%d,%d", &t.qkv_split, &t.proj_split, &t.fc1_split, &t.fc2_split) == 4 && t.qkv_split >= 1 &&
+        t.proj_split >= 1 && t.fc1_split >= 1 && t.fc2_split >= 1)
       g->tiles = t;
   }
   if (cudaGetLastError() != cudaSuccess) {
@@ -280,6 +288,7 @@ int gpt_destroy(Gpt* g) {
   cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
   cudaFree(g->kv);
   cudaFree(g->d_state);
+  cudaFree(g->d_counters);
   if (g->stream) cudaStreamDestroy(g->stream);
   if (g->ev_in) cudaEventDestroy(g->ev_in);
   if (g->ev_out) cudaEventDestroy(g->ev_out);
@@ -390,19 +399,26 @@ int gpt_forward(Gpt* g, const long long* idx, int B, int t, const float* prefix_
 
 namespace {
 
-int decode_gemm(Gpt* g, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, int B, int N, int K, int bn,
-                int split, int epi_direct, void* out, const void* resid, cudaStream_t s) {
+int decode_gemm(Gpt* g, const __nv_bfloat16* X, const __nv_bfloat16* W, const float* bias, int B, int N, int K,
+                int split, int epi_direct, void* out, const void* resid, cudaStream_t s,
+                __nv_bfloat16* gelu_out = nullptr) {
+  // swap-AB: the weights are the 128-row MMA operand, the B batch rows are the MMA N dimension
   GemmArgs a;
   a.stream = s;
   a.pdl = g->pdl;
   a.weights_evict_first = true;
-  a.A = A; a.B = W; a.M = B; a.N = N; a.K = K;
+  a.transpose_out = true;
+  a.A = W; a.B = X; a.M = N; a.N = B; a.K = K;
   a.bias = bias;
   a.out = out;
-  a.bn = bn;
+  a.bn = B <= 32 ? 32 : (B <= 64 ? 64 : (B <= 128 ? 128 : 256));
   if (split > 1) {
     a.epi = EPI_F32_ATOMIC;
     a.split_k = split;
+    if (gelu_out) {   // last split CTA of each feature tile applies GELU and emits the bf16 operand of FC2
+      a.split_counters = g->d_counters;
+      a.finish_out = gelu_out;
+    }
   } else {
     a.epi = epi_direct;
     a.resid = resid;
@@ -415,25 +431,23 @@ int decode_gemm(Gpt* g, const __nv_bfloat16* A, const __nv_bfloat16* W, const fl
 int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int att_T, cudaStream_t s) {
   const int C = g->C;
   const DecodeTiles& tl = g->tiles;
+  const bool qs = tl.qkv_split > 1, fs = tl.fc1_split > 1;
   for (int l = 0; l < g->L; ++l) {
     const GptLayer& w = g->layers[l];
-    const bool qs = tl.qkv_split > 1, fs = tl.fc1_split > 1;
-    MGV_TRY(gpt_layernorm(g->dx, w.ln1_w, w.ln1_b, B, C, g->dln, qs ? g->dqkv32 : nullptr,
-                          qs ? static_cast<long long>(B) * 3 * C : 0, s, g->pdl));
-    MGV_TRY(decode_gemm(g, g->dln, w.wqkv, w.bqkv, B, 3 * C, C, tl.qkv_bn, tl.qkv_split, EPI_F32, g->dqkv32, nullptr, s));
+    MGV_TRY(gpt_layernorm(g->dx, w.ln1_w, w.ln1_b, B, C, g->dln, nullptr, 0, s, g->pdl));
+    MGV_TRY(decode_gemm(g, g->dln, w.wqkv, w.bqkv, B, 3 * C, C, tl.qkv_split, EPI_F32, g->dqkv32, nullptr, s));
     MGV_TRY(gpt_attention_decode(g->dqkv32, B, g->nh, g->d_state, g->kcache(l), g->vcache(l), g->Tmax, g->dy,
-                                 (l == g->L - 1) ? att_out : nullptr, att_T, s, g->pdl));
-    MGV_TRY(decode_gemm(g, g->dy, w.wproj, w.bproj, B, C, C, tl.proj_bn, tl.proj_split, EPI_F32_RESID, g->dx, g->dx, s));
-    MGV_TRY(gpt_layernorm(g->dx, w.ln2_w, w.ln2_b, B, C, g->dln, fs ? g->dh32 : nullptr,
-                          fs ? static_cast<long long>(B) * 4 * C : 0, s, g->pdl));
+                                 (l == g->L - 1) ? att_out : nullptr, att_T, qs, s, g->pdl));
+    MGV_TRY(decode_gemm(g, g->dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, g->dx, g->dx, s));
+    MGV_TRY(gpt_layernorm(g->dx, w.ln2_w, w.ln2_b, B, C, g->dln, nullptr, 0, s, g->pdl));
     if (fs) {
-      MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_bn, tl.fc1_split, EPI_F32, g->dh32, nullptr, s));
-      MGV_TRY(gpt_gelu_bf16(g->dh32, static_cast<long long>(B) * 4 * C, g->dh, s, g->pdl));
+      MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_split, EPI_F32, g->dh32, nullptr, s));
+      MGV_TRY(gpt_gelu_bf16(g->dh32, static_cast<long long>(B) * 4 * C, g->dh, true, s, g->pdl));
       g->launches += 1;
     } else {
-      MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_bn, 1, EPI_BF16_GELU, g->dh, nullptr, s));
+      MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, 1, EPI_BF16_GELU, g->dh, nullptr, s));
     }
-    MGV_TRY(decode_gemm(g, g->dh, w.wfc2, w.bfc2, B, C, 4 * C, tl.fc2_bn, tl.fc2_split, EPI_F32_RESID, g->dx, g->dx, s));
+    MGV_TRY(decode_gemm(g, g->dh, w.wfc2, w.bfc2, B, C, 4 * C, tl.fc2_split, EPI_F32_RESID, g->dx, g->dx, s));
     g->launches += 3;
   }
   MGV_TRY(gpt_sample_step(sa, s, g->pdl));
@@ -492,6 +506,9 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   MGV_TRY(gpt_embed(x0, B, 1, T0 - 1, t0, prefix_emb, cls, g->embedder, m, g->tok_emb, g->pos_emb, g->C, g->V,
                     g->cfg.class_size, g->dx, g->d_state + 2, s, false));
   g->launches += 1;
+  // split-K accumulators start at zero; afterwards their consumers clear them for the next layer / position
+  MGV_CHECK_CUDA(cudaMemsetAsync(g->dqkv32, 0, static_cast<size_t>(B) * 3 * g->C * 4, s));
+  MGV_CHECK_CUDA(cudaMemsetAsync(g->dh32, 0, static_cast<size_t>(B) * 4 * g->C * 4, s));
   const int init_state[2] = {T0 - 1, 0};
   MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state, init_state, 2 * sizeof(int), cudaMemcpyHostToDevice, s));
 

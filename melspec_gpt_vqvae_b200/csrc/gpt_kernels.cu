@@ -11,8 +11,8 @@ __global__ void embed_kernel(const long long* __restrict__ idx, int R, int p_off
                              const float* __restrict__ embedder, int m, const float* __restrict__ tok_emb,
                              const float* __restrict__ pos_emb, int C, int vocab, int class_size,
                              float* __restrict__ x_out, int* __restrict__ err_flag) {
-  pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents();   // dependents may start their prologue / weight prefetch now
+  pdl_wait();                // ... but our inputs need the upstream grid
   const int row = blockIdx.x;  // b*R + r
   const int b = row / R, p = p_off + (row - b * R);
   const float* src;
@@ -50,15 +50,10 @@ constexpr int LN_MAX_V4 = 16;  // C <= 2048
 __global__ void __launch_bounds__(128)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bia, int rows, int C,
                  __nv_bfloat16* __restrict__ out, float* __restrict__ zero_buf, long long zero_count) {
-  pdl_wait();
-  pdl_launch_dependents();
-  if (zero_buf) {
-    const long long n4 = zero_count / 4;
-    float4* z4 = reinterpret_cast<float4*>(zero_buf);
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-      z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  pdl_launch_dependents();   // dependents may start their prologue / weight prefetch now
+  pdl_wait();                // ... but our inputs need the upstream grid
+  (void)zero_buf;
+  (void)zero_count;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
   if (row >= rows) return;
@@ -219,65 +214,113 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T, int nh,
 }
 
 // ------------------------------------------------------------------ decode attention
+// One CTA per (sequence, head), 128 threads = 16 key groups x 8 dim chunks: thread (kg, dc) owns the 8
+// head dims [8*dc, 8*dc+8) (one 16-byte load per key) of keys kg, kg+16, ... ; keys are walked in passes of
+// 128 (8 independent loads per thread in flight).  A warp's load covers 4 consecutive 128-byte cache rows
+// (512 contiguous bytes).  <= 64 registers and ~2 KB smem so that all B*n_head CTAs are resident in ONE wave
+// (7 per SM at B=64): the step's latency is then one dependency chain, not one per wave.  The V loads of the
+// first pass are issued before the softmax reductions.
 constexpr int AD_THREADS = 128;
+constexpr int AD_KG = 16;                 // key groups
+constexpr int AD_KPP = 8;                 // keys per thread per pass
+constexpr int AD_PASS = AD_KG * AD_KPP;   // 128 keys per pass
 
-__global__ void __launch_bounds__(AD_THREADS)
-attn_decode_kernel(const float* __restrict__ qkv32, int nh, const int* __restrict__ pos_ptr,
+__global__ void __launch_bounds__(AD_THREADS, 7)
+attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ pos_ptr,
                    __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache, int Tmax,
-                   __nv_bfloat16* __restrict__ y, float* __restrict__ att_rows, int Tatt) {
-  pdl_wait();
+                   __nv_bfloat16* __restrict__ y, float* __restrict__ att_rows, int Tatt, int zero_consumed) {
   pdl_launch_dependents();
-  __shared__ float sq[GPT_HEAD_DIM];
-  __shared__ float sk[GPT_HEAD_DIM];
-  __shared__ float sv[GPT_HEAD_DIM];
+  __shared__ __align__(16) float sq[GPT_HEAD_DIM];
+  __shared__ __align__(16) __nv_bfloat16 sk[GPT_HEAD_DIM];
+  __shared__ __align__(16) __nv_bfloat16 sv[GPT_HEAD_DIM];
   __shared__ float ss[GPT_MAX_T];
   __shared__ float red[8];
   __shared__ float sacc[4][GPT_HEAD_DIM];
   const int bh = blockIdx.x;
   const int b = bh / nh, h = bh - b * nh;
   const int C = nh * GPT_HEAD_DIM;
-  const int pos = *pos_ptr;
+  const int pos = *pos_ptr;   // written by an earlier decode step (not by the upstream grid)
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  __nv_bfloat16* kc = kcache + (static_cast<long long>(b) * nh + h) * Tmax * GPT_HEAD_DIM;
-  __nv_bfloat16* vc = vcache + (static_cast<long long>(b) * nh + h) * Tmax * GPT_HEAD_DIM;
+  const int kg = t >> 3, dc = t & 7;
+  const __nv_bfloat16* kc = kcache + (static_cast<long long>(b) * nh + h) * Tmax * GPT_HEAD_DIM + dc * 8;
+  const __nv_bfloat16* vc = vcache + (static_cast<long long>(b) * nh + h) * Tmax * GPT_HEAD_DIM + dc * 8;
+  const int npass = pos / AD_PASS + 1;
 
+  // ---- first pass of K rows: positions < pos were written by earlier steps, so load before the dependency
+  uint4 kreg[AD_KPP];
+#pragma unroll
+  for (int i = 0; i < AD_KPP; ++i) {
+    const int j = kg + AD_KG * i;
+    kreg[i] = make_uint4(0, 0, 0, 0);
+    if (j < pos) kreg[i] = *reinterpret_cast<const uint4*>(kc + static_cast<long long>(j) * GPT_HEAD_DIM);
+  }
+  pdl_wait();
   if (t < GPT_HEAD_DIM) {
-    const float* base = qkv32 + static_cast<long long>(b) * 3 * C + h * GPT_HEAD_DIM + t;
+    float* base = qkv32 + static_cast<long long>(b) * 3 * C + h * GPT_HEAD_DIM + t;
     // q is rounded to bf16 like the prefill path (which stores q,k,v as bf16)
     sq[t] = __bfloat162float(__float2bfloat16(base[0]));
     const __nv_bfloat16 kb = __float2bfloat16(base[C]);
     const __nv_bfloat16 vb = __float2bfloat16(base[2 * C]);
-    sk[t] = __bfloat162float(kb);
-    sv[t] = __bfloat162float(vb);
-    kc[static_cast<long long>(pos) * GPT_HEAD_DIM + t] = kb;
-    vc[static_cast<long long>(pos) * GPT_HEAD_DIM + t] = vb;
+    if (zero_consumed) {  // the next layer's split-K QKV GEMM accumulates into this buffer with atomics
+      base[0] = 0.f;
+      base[C] = 0.f;
+      base[2 * C] = 0.f;
+    }
+    sk[t] = kb;
+    sv[t] = vb;
+    const long long co = (static_cast<long long>(b) * nh + h) * Tmax * GPT_HEAD_DIM + static_cast<long long>(pos) * GPT_HEAD_DIM + t;
+    kcache[co] = kb;
+    vcache[co] = vb;
   }
   __syncthreads();
 
+  // ---- scores
   const float scale = 1.0f / sqrtf(static_cast<float>(GPT_HEAD_DIM));
+  float q8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q8[e] = sq[dc * 8 + e];
   float lmax = -INFINITY;
-  for (int j = t; j <= pos; j += AD_THREADS) {
-    float s = 0.f;
-    if (j < pos) {
-      const uint4* kr = reinterpret_cast<const uint4*>(kc + static_cast<long long>(j) * GPT_HEAD_DIM);
+  for (int p = 0; p < npass; ++p) {
+    if (p > 0) {
 #pragma unroll
-      for (int part = 0; part < 8; ++part) {
-        const uint4 q4 = kr[part];
-        const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 kf = unpack_bf16x2(w[e]);
-          s = fmaf(sq[part * 8 + 2 * e], kf.x, s);
-          s = fmaf(sq[part * 8 + 2 * e + 1], kf.y, s);
-        }
+      for (int i = 0; i < AD_KPP; ++i) {
+        const int j = p * AD_PASS + kg + AD_KG * i;
+        kreg[i] = make_uint4(0, 0, 0, 0);
+        if (j < pos) kreg[i] = *reinterpret_cast<const uint4*>(kc + static_cast<long long>(j) * GPT_HEAD_DIM);
       }
-    } else {
-#pragma unroll 8
-      for (int d = 0; d < GPT_HEAD_DIM; ++d) s = fmaf(sq[d], sk[d], s);
     }
-    s *= scale;
-    ss[j] = s;
-    lmax = fmaxf(lmax, s);
+#pragma unroll
+    for (int i = 0; i < AD_KPP; ++i) {
+      const int j = p * AD_PASS + kg + AD_KG * i;
+      uint4 kv = kreg[i];
+      if (j == pos) kv = *reinterpret_cast<const uint4*>(sk + dc * 8);
+      const float2 a = unpack_bf16x2(kv.x), bq = unpack_bf16x2(kv.y), c = unpack_bf16x2(kv.z), d = unpack_bf16x2(kv.w);
+      float s = q8[0] * a.x;
+      s = fmaf(q8[1], a.y, s);
+      s = fmaf(q8[2], bq.x, s);
+      s = fmaf(q8[3], bq.y, s);
+      s = fmaf(q8[4], c.x, s);
+      s = fmaf(q8[5], c.y, s);
+      s = fmaf(q8[6], d.x, s);
+      s = fmaf(q8[7], d.y, s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s *= scale;
+      if (j <= pos) {
+        if (dc == 0) ss[j] = s;
+        lmax = fmaxf(lmax, s);
+      }
+    }
+  }
+  // ---- V rows of the first pass: issue now, consume after the softmax reductions
+  uint4 vreg[AD_KPP];
+#pragma unroll
+  for (int i = 0; i < AD_KPP; ++i) {
+    const int j = kg + AD_KG * i;
+    vreg[i] = make_uint4(0, 0, 0, 0);
+    if (j < pos) vreg[i] = *reinterpret_cast<const uint4*>(vc + static_cast<long long>(j) * GPT_HEAD_DIM);
+    else if (j == pos) vreg[i] = *reinterpret_cast<const uint4*>(sv + dc * 8);
   }
   lmax = warp_max(lmax);
   if (lane == 0) red[warp] = lmax;
@@ -293,41 +336,67 @@ attn_decode_kernel(const float* __restrict__ qkv32, int nh, const int* __restric
   if (lane == 0) red[4 + warp] = lsum;
   __syncthreads();
   const float inv = 1.0f / ((red[4] + red[5]) + (red[6] + red[7]));
-  if (att_rows) {
+  if (att_rows && pos < Tatt) {
     float* arow = att_rows + ((static_cast<long long>(b) * nh + h) * Tatt + pos) * Tatt;
-    if (pos < Tatt)
-      for (int j = t; j <= pos; j += AD_THREADS) arow[j] = ss[j] * inv;
+    for (int j = t; j <= pos; j += AD_THREADS) arow[j] = ss[j] * inv;
   }
-  // PV: lane -> dims (2*lane, 2*lane+1); warp -> keys j = warp, warp+4, ...
-  float a0 = 0.f, a1 = 0.f;
-  for (int j = warp; j <= pos; j += 4) {
-    const float p = ss[j];
-    float2 vf;
-    if (j < pos)
-      vf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vc + static_cast<long long>(j) * GPT_HEAD_DIM + 2 * lane));
-    else
-      vf = make_float2(sv[2 * lane], sv[2 * lane + 1]);
-    a0 = fmaf(p, vf.x, a0);
-    a1 = fmaf(p, vf.y, a1);
+  // ---- PV
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = 0; p < npass; ++p) {
+    if (p > 0) {
+#pragma unroll
+      for (int i = 0; i < AD_KPP; ++i) {
+        const int j = p * AD_PASS + kg + AD_KG * i;
+        vreg[i] = make_uint4(0, 0, 0, 0);
+        if (j < pos) vreg[i] = *reinterpret_cast<const uint4*>(vc + static_cast<long long>(j) * GPT_HEAD_DIM);
+        else if (j == pos) vreg[i] = *reinterpret_cast<const uint4*>(sv + dc * 8);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < AD_KPP; ++i) {
+      const int j = p * AD_PASS + kg + AD_KG * i;
+      if (j <= pos) {
+        const float pj = ss[j];
+        const float2 a = unpack_bf16x2(vreg[i].x), bq = unpack_bf16x2(vreg[i].y), c = unpack_bf16x2(vreg[i].z),
+                     d = unpack_bf16x2(vreg[i].w);
+        acc[0] = fmaf(pj, a.x, acc[0]);
+        acc[1] = fmaf(pj, a.y, acc[1]);
+        acc[2] = fmaf(pj, bq.x, acc[2]);
+        acc[3] = fmaf(pj, bq.y, acc[3]);
+        acc[4] = fmaf(pj, c.x, acc[4]);
+        acc[5] = fmaf(pj, c.y, acc[5]);
+        acc[6] = fmaf(pj, d.x, acc[6]);
+        acc[7] = fmaf(pj, d.y, acc[7]);
+      }
+    }
   }
-  sacc[warp][2 * lane] = a0;
-  sacc[warp][2 * lane + 1] = a1;
+  // reduce the 4 key groups of a warp (lanes with equal dc), then the 4 warps through smem
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sacc[warp][lane * 8 + e] = acc[e];
+  }
   __syncthreads();
   if (t < GPT_HEAD_DIM) {
-    const float o = ((sacc[0][t] + sacc[1][t]) + (sacc[2][t] + sacc[3][t])) * inv;
-    y[static_cast<long long>(b) * C + h * GPT_HEAD_DIM + t] = __float2bfloat16(o);
+    const float o = (sacc[0][t] + sacc[1][t]) + (sacc[2][t] + sacc[3][t]);
+    y[static_cast<long long>(b) * C + h * GPT_HEAD_DIM + t] = __float2bfloat16(o * inv);
   }
 }
 
 // ------------------------------------------------------------------ GELU (split-K FC1 path)
-__global__ void gelu_bf16_kernel(const float* __restrict__ h32, long long n4, __nv_bfloat16* __restrict__ out) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const float4* i4 = reinterpret_cast<const float4*>(h32);
+__global__ void gelu_bf16_kernel(float* __restrict__ h32, long long n4, __nv_bfloat16* __restrict__ out, int zero_consumed) {
+  pdl_launch_dependents();   // dependents may start their prologue / weight prefetch now
+  pdl_wait();                // ... but our inputs need the upstream grid
+  float4* i4 = reinterpret_cast<float4*>(h32);
   uint2* o2 = reinterpret_cast<uint2*>(out);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = i4[i];
+    if (zero_consumed) i4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // next layer's split-K FC1 accumulates here
     o2[i] = make_uint2(pack_bf16x2(gelu_erf(v.x), gelu_erf(v.y)), pack_bf16x2(gelu_erf(v.z), gelu_erf(v.w)));
   }
 }
@@ -369,8 +438,8 @@ __device__ float block_reduce(float v, float* red, bool is_max) {
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_step_kernel(const SampleArgs a) {
   unsigned int* done_counter = a.done_counter;
-  pdl_wait();
-  pdl_launch_dependents();
+  pdl_launch_dependents();   // dependents may start their prologue / weight prefetch now
+  pdl_wait();                // ... but our inputs need the upstream grid
   extern __shared__ float sm_s[];
   float* sx = sm_s;            // [C]
   float* sl = sx + a.C;        // [V]
@@ -548,25 +617,25 @@ int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_
   return MGV_OK;
 }
 
-int gpt_attention_decode(const float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
-                         __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, cudaStream_t s,
-                         bool pdl) {
+int gpt_attention_decode(float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
+                         __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, bool zero_consumed,
+                         cudaStream_t s, bool pdl) {
   MGV_REQUIRE(Tmax <= GPT_MAX_T, "attention: Tmax=%d exceeds %d", Tmax, GPT_MAX_T);
   if (B == 0) return MGV_OK;
   LaunchCfg lc(dim3(B * nh), dim3(AD_THREADS), 0, s, pdl);
   MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_kernel, qkv32, nh, pos_ptr, kcache, vcache, Tmax, y, att_rows,
-                                    Tatt));
+                                    Tatt, zero_consumed ? 1 : 0));
   return MGV_OK;
 }
 
-int gpt_gelu_bf16(const float* h32, long long n, __nv_bfloat16* out, cudaStream_t s, bool pdl) {
+int gpt_gelu_bf16(float* h32, long long n, __nv_bfloat16* out, bool zero_consumed, cudaStream_t s, bool pdl) {
   MGV_REQUIRE(n % 4 == 0, "gelu: n");
   if (n == 0) return MGV_OK;
   const long long n4 = n / 4;
   int blocks = static_cast<int>((n4 + 255) / 256);
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
   LaunchCfg lc(dim3(blocks), dim3(256), 0, s, pdl);
-  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gelu_bf16_kernel, h32, n4, out));
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gelu_bf16_kernel, h32, n4, out, zero_consumed ? 1 : 0));
   return MGV_OK;
 }
 

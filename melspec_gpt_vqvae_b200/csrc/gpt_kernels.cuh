@@ -15,8 +15,7 @@ int gpt_embed(const long long* idx, int B, int R, int p_off, int idx_ld, const f
               const float* embedder, int m, const float* tok_emb, const float* pos_emb, int C, int vocab,
               int class_size, float* x_out, int* err_flag, cudaStream_t s, bool pdl);
 
-// LayerNorm (eps 1e-5, affine) fp32 rows -> bf16 rows; optionally zero-fills `zero_buf`
-// (the split-K accumulation buffer of the GEMM that follows).
+// LayerNorm (eps 1e-5, affine) fp32 rows -> bf16 rows (zero_buf / zero_count: unused, kept for ABI stability).
 int gpt_layernorm(const float* x, const float* w, const float* b, int rows, int C, __nv_bfloat16* out, float* zero_buf,
                   long long zero_count, cudaStream_t s, bool pdl);
 
@@ -29,12 +28,13 @@ int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_
 
 // One decode position: q,k,v fp32 [B, 3C] for position *pos_ptr; appends k,v to the cache and
 // attends over positions 0..pos.  att_rows (optional): fp32 [B, nh, Tatt, Tatt] pre-zeroed; entries 0..pos of row pos are written.
-int gpt_attention_decode(const float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
-                         __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, cudaStream_t s,
-                         bool pdl);
+// zero_consumed: the q,k,v accumulators are cleared after they are read (ready for the next split-K reduction).
+int gpt_attention_decode(float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
+                         __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, bool zero_consumed,
+                         cudaStream_t s, bool pdl);
 
 // h = gelu_erf(h32) as bf16 (split-K FC1 path)
-int gpt_gelu_bf16(const float* h32, long long n, __nv_bfloat16* out, cudaStream_t s, bool pdl);
+int gpt_gelu_bf16(float* h32, long long n, __nv_bfloat16* out, bool zero_consumed, cudaStream_t s, bool pdl);
 
 struct SampleArgs {
   const float* x;          // [B, C] final residual stream of the step

@@ -242,6 +242,20 @@ int mgv_test_gemm(int impl, const void* A, const void* B, int M, int N, int K, i
   MGV_API_END
 }
 
+int mgv_test_gemm_swapab(int impl, const void* W, const void* X, int M, int N, int K, int epi, const float* bias,
+                         void* out, const void* resid, int bn, int split_k, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  MGV_TRY(check_device());
+  GemmArgs a;
+  a.A = W; a.B = X; a.M = M; a.N = N; a.K = K;
+  a.epi = epi; a.bias = bias; a.out = out; a.resid = resid;
+  a.bn = bn; a.split_k = split_k;
+  a.transpose_out = true;
+  a.stream = static_cast<cudaStream_t>(stream);
+  return impl == 0 ? gemm_bf16_tc(a) : gemm_bf16_ref(a);
+  MGV_API_END
+}
+
 int mgv_test_conv3x3(int impl, const void* x, const void* w, const float* bias, int n_img, int Hin, int Win, int Cin,
                      int Cout, int stride, void* out, const void* resid, mgv_stream_t stream) {
   MGV_API_BEGIN

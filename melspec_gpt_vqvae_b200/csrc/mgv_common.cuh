@@ -47,6 +47,7 @@ const char* get_error();
 int check_device();      // MGV_OK iff the current device is compute capability 10.x
 int num_sms();
 
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

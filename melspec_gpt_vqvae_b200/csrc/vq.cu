@@ -272,8 +272,9 @@ __global__ void vq_gather_kernel(const long long* __restrict__ idx, const float*
 
 int vq_argmin(const float* z, const float* codebook, int B, int D, int HW, int K, long long* idx_out, float* dmin_out,
               cudaStream_t stream) {
-  MGV_REQUIRE(z && codebook && idx_out, "vq_argmin: null pointer");
   MGV_REQUIRE(B >= 0 && HW > 0, "vq_argmin: B=%d HW=%d", B, HW);
+  if (B == 0) return MGV_OK;   // empty batch: nothing to do (pointers may be null)
+  MGV_REQUIRE(z && codebook && idx_out, "vq_argmin: null pointer");
   MGV_REQUIRE(K >= 1 && K <= VQ_MAX_K, "vq_argmin: num_embeddings=%d unsupported (1..%d)", K, VQ_MAX_K);
   MGV_REQUIRE(D >= VQ_KC && D % VQ_KC == 0 && D <= 256, "vq_argmin: embedding_dim=%d must be 64, 128, 192 or 256", D);
   if (B == 0) return MGV_OK;
@@ -294,8 +295,8 @@ int vq_argmin(const float* z, const float* codebook, int B, int D, int HW, int K
 int vq_finish(const float* z, const float* codebook, const long long* idx, int B, int D, int HW, int K,
               float commitment_cost, float* quantized, float* encodings, float* loss_out, float* perplexity_out,
               void* workspace /* >= 8 + 4*K bytes, 8-byte aligned */, cudaStream_t stream) {
-  MGV_REQUIRE(z && codebook && idx && workspace, "vq_finish: null pointer");
   if (B == 0) return MGV_OK;
+  MGV_REQUIRE(z && codebook && idx && workspace, "vq_finish: null pointer");
   double* sq = static_cast<double*>(workspace);
   unsigned int* counts = reinterpret_cast<unsigned int*>(sq + 1);
   MGV_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 8 + 4 * static_cast<size_t>(K), stream));
@@ -313,9 +314,9 @@ int vq_finish(const float* z, const float* codebook, const long long* idx, int B
 
 int vq_gather(const long long* idx, const float* codebook, long long n_vec, int D, int HW, int K, float* out,
               int* bad_index_flag, cudaStream_t stream) {
-  MGV_REQUIRE(idx && codebook && out, "vq_gather: null pointer");
   MGV_REQUIRE(HW >= 0 && (HW == 0 || n_vec % HW == 0), "vq_gather: n_vec=%lld not a multiple of HW=%d", n_vec, HW);
   if (n_vec == 0) return MGV_OK;
+  MGV_REQUIRE(idx && codebook && out, "vq_gather: null pointer");
   const long long total = n_vec * D;
   int blocks = static_cast<int>((total + 255) / 256);
   const int cap = num_sms() * 8;

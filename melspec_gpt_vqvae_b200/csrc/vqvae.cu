@@ -7,6 +7,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <stdlib.h>
 #include "gemm_tc.cuh"
 #include "vqvae.cuh"
 #include "vqvae_kernels.cuh"
@@ -22,6 +23,7 @@ constexpr int NUM_RES_BLOCKS = 2;
 constexpr int Z_CH = 256;
 constexpr int MEL_H = 80, MEL_W = 848;
 constexpr int LAT_H = 5, LAT_W = 53;
+constexpr int MAX_TILES_PER_IMAGE = 80 * 7;   // 80x848 output: 7 x-tiles of 128 pixels per row
 
 struct Conv {   // 3x3 or 1x1 convolution, weights [Cout][taps][Cin] bf16
   __nv_bfloat16* w = nullptr;
@@ -102,7 +104,8 @@ struct Vqvae {
   int ws_B = 0;
   __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float* f32buf = nullptr;     // [B,265,256] fp32 (encoder output before NCHW transpose)
-  float* gn_slab = nullptr;    // per-GroupNorm statistics slots [slot][B][32][2]
+  float* gn_slab = nullptr;    // per-GroupNorm finalized statistics slots [slot][B][32][{mean, rstd}]
+  float* gn_part = nullptr;    // per-tile partial sums of the tensor produced last [B][tiles][32][2] (reused)
   int gn_slots = 0;
   int* flag = nullptr;
   long long launches = 0;
@@ -215,12 +218,14 @@ int ensure_ws(Vqvae* v, int B) {
   for (auto& p : v->buf) { cudaFree(p); p = nullptr; }
   cudaFree(v->f32buf); v->f32buf = nullptr;
   cudaFree(v->gn_slab); v->gn_slab = nullptr;
+  cudaFree(v->gn_part); v->gn_part = nullptr;
   v->ws_B = 0;
   const size_t act = static_cast<size_t>(B) * MEL_H * MEL_W * CH;  // largest activation (elements)
   for (auto& p : v->buf) MGV_CHECK_CUDA(cudaMalloc(&p, act * 2));
   MGV_CHECK_CUDA(cudaMalloc(&v->f32buf, static_cast<size_t>(B) * LAT_H * LAT_W * (v->D > Z_CH ? v->D : Z_CH) * 4));
   v->gn_slots = 96;
   MGV_CHECK_CUDA(cudaMalloc(&v->gn_slab, static_cast<size_t>(v->gn_slots) * B * 64 * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&v->gn_part, static_cast<size_t>(B) * MAX_TILES_PER_IMAGE * 64 * 4));
   v->ws_B = B;
   return MGV_OK;
 }
@@ -250,6 +255,16 @@ struct Ctx {
   }
 };
 
+int conv_stages() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MGV_CONV_STAGES");
+    v = e ? atoi(e) : 2;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 // 3x3 conv (stride 1 pad 1, or the Downsample variant) with optional residual and fused GN statistics of the output
 int conv3(Ctx& c, const Conv& w, const __nv_bfloat16* x, int Hin, int Win, int stride, __nv_bfloat16* out,
           const __nv_bfloat16* resid, float* stats_out) {
@@ -263,10 +278,21 @@ int conv3(Ctx& c, const Conv& w, const __nv_bfloat16* x, int Hin, int Win, int s
   a.epi = resid ? EPI_BF16_RESID : EPI_BF16;
   a.bias = w.b; a.out = out; a.resid = resid;
   a.bn = 128;
-  if (stats_out) { a.gn_sum = stats_out; a.gn_group_ch = w.cout / 32; }
+  a.max_stages = conv_stages();   // 2 stages = 64 KB -> three CTAs per SM: epilogues overlap the other CTAs' MMAs
+  if (stats_out) { a.gn_sum = c.v->gn_part; a.gn_group_ch = w.cout / 32; }
   a.stream = c.s;
   c.v->launches++;
-  return gemm_bf16_tc(a);
+  MGV_TRY(gemm_bf16_tc(a));
+  if (stats_out) {
+    // tiles per image of the conv kernel's grid (see fill_params in gemm_tc.cu)
+    int wb = 16;
+    while (wb < 128 && wb < a.W) wb *= 2;
+    const int tiles = ceil_div(a.W, wb) * ceil_div(a.H, 128 / wb);
+    MGV_REQUIRE(tiles <= MAX_TILES_PER_IMAGE, "conv3: %d tiles per image exceed the statistics scratch", tiles);
+    MGV_TRY(vqvae_gn_finalize(c.v->gn_part, c.B, tiles, static_cast<float>(a.H) * a.W * (w.cout / 32), stats_out, c.s));
+    c.v->launches++;
+  }
+  return MGV_OK;
 }
 
 // 1x1 conv == GEMM over NHWC pixels
@@ -276,9 +302,25 @@ int conv1(Ctx& c, const __nv_bfloat16* wmat, const float* bias, int cin, int cou
   a.A = x; a.B = wmat; a.M = static_cast<int>(rows); a.N = cout; a.K = cin;
   a.epi = epi; a.bias = bias; a.out = out; a.resid = resid;
   a.bn = 128;
+  a.max_stages = conv_stages();
   a.stream = c.s;
   c.v->launches++;
   return gemm_bf16_tc(a);
+}
+
+// GroupNorm apply (+ optional swish) from accumulated statistics
+int gn(Ctx& c, const GN& g, const __nv_bfloat16* x, const float* stats, int HW, int do_swish, __nv_bfloat16* y) {
+  c.v->launches += 1;
+  return vqvae_gn_apply(x, stats, g.w, g.b, c.B, HW, g.c, do_swish, y, c.s);
+}
+
+// statistics of a tensor that was not produced by a conv epilogue (attention output, encoder conv_in)
+int stats_of(Ctx& c, const __nv_bfloat16* x, int HW, int C, float* stats_out) {
+  int tiles = 0;
+  MGV_TRY(vqvae_gn_stats(x, c.B, HW, C, c.v->gn_part, &tiles, c.s));
+  MGV_REQUIRE(tiles <= MAX_TILES_PER_IMAGE, "gn_stats: too many chunks");
+  c.v->launches += 2;
+  return vqvae_gn_finalize(c.v->gn_part, c.B, tiles, static_cast<float>(HW) * (C / 32), stats_out, c.s);
 }
 
 // ResnetBlock.forward (:114-135).  x (with statistics x_stats) -> out (statistics out_stats).
@@ -286,17 +328,16 @@ int conv1(Ctx& c, const __nv_bfloat16* wmat, const float* bias, int cin, int cou
 int resblock(Ctx& c, const ResBlock& r, const __nv_bfloat16* x, const float* x_stats, int H, int W, __nv_bfloat16* out,
              float* out_stats, __nv_bfloat16* tmp_a, __nv_bfloat16* tmp_b, __nv_bfloat16* tmp_s) {
   const int HW = H * W;
-  MGV_TRY(vqvae_gn_apply(x, x_stats, r.n1.w, r.n1.b, c.B, HW, r.n1.c, 1, tmp_a, c.s));
+  MGV_TRY(gn(c, r.n1, x, x_stats, HW, 1, tmp_a));
   float* st1 = c.new_stats();
   MGV_TRY(conv3(c, r.c1, tmp_a, H, W, 1, tmp_b, nullptr, st1));
-  MGV_TRY(vqvae_gn_apply(tmp_b, st1, r.n2.w, r.n2.b, c.B, HW, r.n2.c, 1, tmp_a, c.s));
+  MGV_TRY(gn(c, r.n2, tmp_b, st1, HW, 1, tmp_a));
   const __nv_bfloat16* shortcut = x;
   if (r.has_nin) {
     MGV_TRY(conv1(c, r.nin.w, r.nin.b, r.nin.cin, r.nin.cout, x, static_cast<long long>(c.B) * HW, tmp_s, EPI_BF16, nullptr));
     shortcut = tmp_s;
   }
   MGV_TRY(conv3(c, r.c2, tmp_a, H, W, 1, out, shortcut, out_stats));
-  c.v->launches += 2;
   return MGV_OK;
 }
 
@@ -305,15 +346,12 @@ int attnblock(Ctx& c, const Attn& a, const __nv_bfloat16* x, const float* x_stat
               float* out_stats, __nv_bfloat16* tmp_a, __nv_bfloat16* tmp_b) {
   const int HW = H * W, C = a.n.c;
   const long long rows = static_cast<long long>(c.B) * HW;
-  MGV_TRY(vqvae_gn_apply(x, x_stats, a.n.w, a.n.b, c.B, HW, C, 0, tmp_a, c.s));
+  MGV_TRY(gn(c, a.n, x, x_stats, HW, 0, tmp_a));
   MGV_TRY(conv1(c, a.wqkv, a.bqkv, C, 3 * C, tmp_a, rows, tmp_b, EPI_BF16, nullptr));   // q | k | v
   MGV_TRY(vqvae_spatial_attention(tmp_b, c.B, HW, C, tmp_a, c.s));
   MGV_TRY(conv1(c, a.proj.w, a.proj.b, C, C, tmp_a, rows, out, EPI_BF16_RESID, x));
-  if (out_stats) {
-    MGV_TRY(vqvae_gn_stats(out, c.B, HW, C, out_stats, c.s));
-    c.v->launches++;
-  }
-  c.v->launches += 2;
+  if (out_stats) MGV_TRY(stats_of(c, out, HW, C, out_stats));
+  c.v->launches += 1;
   return MGV_OK;
 }
 
@@ -353,6 +391,7 @@ int vqvae_destroy(Vqvae* v) {
   for (auto& p : v->buf) cudaFree(p);
   cudaFree(v->f32buf);
   cudaFree(v->gn_slab);
+  cudaFree(v->gn_part);
   cudaFree(v->flag);
   delete v;
   return MGV_OK;
@@ -413,7 +452,6 @@ int vqvae_decode(Vqvae* v, const long long* idx, const float* quant_bchw, int B,
   v->launches = 0;
   MGV_TRY(ensure_ws(v, B));
   Ctx c{v, B, s};
-  MGV_CHECK_CUDA(cudaMemsetAsync(v->gn_slab, 0, static_cast<size_t>(v->gn_slots) * B * 64 * 4, s));
   __nv_bfloat16 *h = v->buf[0], *o = v->buf[1], *ta = v->buf[2], *tb = v->buf[3], *ts = v->buf[4];
   const long long lat_rows = static_cast<long long>(B) * LAT_H * LAT_W;
   // ---- z_q -> post_quant_conv (fused into a table lookup when decoding codes)
@@ -470,7 +508,7 @@ int vqvae_decode(Vqvae* v, const long long* idx, const float* quant_bchw, int B,
   // ---- end (:389-391)
   MGV_TRY(vqvae_norm_swish_conv_out(h, st, v->dec_norm_out.w, v->dec_norm_out.b, v->dec_conv_out_w, v->dec_conv_out_b, B,
                                     H, W, CH, mel_out, s));
-  v->launches++;
+  v->launches += 1;
   if (idx) {
     int flag = 0;
     MGV_CHECK_CUDA(cudaMemcpyAsync(&flag, v->flag, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -493,13 +531,12 @@ int vqvae_encode(Vqvae* v, const float* mel, int B, float* z_out, cudaStream_t s
   v->launches = 0;
   MGV_TRY(ensure_ws(v, B));
   Ctx c{v, B, s};
-  MGV_CHECK_CUDA(cudaMemsetAsync(v->gn_slab, 0, static_cast<size_t>(v->gn_slots) * B * 64 * 4, s));
   __nv_bfloat16 *h = v->buf[0], *o = v->buf[1], *ta = v->buf[2], *tb = v->buf[3], *ts = v->buf[4];
   int H = MEL_H, W = MEL_W;
   MGV_TRY(vqvae_conv_in_1ch(mel, v->enc_conv_in_w, v->enc_conv_in_b, B, H, W, CH, h, s));        // :261
   float* st = c.new_stats();
-  MGV_TRY(vqvae_gn_stats(h, B, H * W, CH, st, s));
-  v->launches += 2;
+  MGV_TRY(stats_of(c, h, H * W, CH, st));
+  v->launches += 1;
   float* st2;
   for (int lvl = 0; lvl < NUM_RES; ++lvl) {
     for (int b = 0; b < NUM_RES_BLOCKS; ++b) {
@@ -531,7 +568,7 @@ int vqvae_encode(Vqvae* v, const float* mel, int B, float* z_out, cudaStream_t s
   MGV_REQUIRE(c.next_slot <= v->gn_slots, "vqvae_encode: statistics slots exhausted");
   MGV_REQUIRE(H == LAT_H && W == LAT_W, "vqvae_encode: unexpected latent size %dx%d", H, W);
   // ---- end (:278-280) + quant_conv (:606)
-  MGV_TRY(vqvae_gn_apply(h, st, v->enc_norm_out.w, v->enc_norm_out.b, B, H * W, v->enc_norm_out.c, 1, ta, s));
+  MGV_TRY(gn(c, v->enc_norm_out, h, st, H * W, 1, ta));
   MGV_TRY(conv3(c, v->enc_conv_out, ta, H, W, 1, tb, nullptr, nullptr));
   const long long rows = static_cast<long long>(B) * H * W;
   MGV_TRY(conv1(c, v->quant_conv.w, v->quant_conv.b, Z_CH, v->D, tb, rows, v->f32buf, EPI_F32, nullptr));

@@ -86,7 +86,7 @@ __global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ in, int N, int
 // ------------------------------------------------------------------ GroupNorm
 // grid (chunks, N); block 256; every thread owns a fixed channel octet (256 % (C/8) == 0)
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const uint4* __restrict__ x, int HW, int C, float* __restrict__ sums) {
+gn_stats_kernel(const uint4* __restrict__ x, int HW, int C, float* __restrict__ part) {
   __shared__ float sh[GN_GROUPS * 2];
   if (threadIdx.x < GN_GROUPS * 2) sh[threadIdx.x] = 0.f;
   __syncthreads();
@@ -112,15 +112,38 @@ gn_stats_kernel(const uint4* __restrict__ x, int HW, int C, float* __restrict__ 
   atomicAdd(&sh[2 * g1], s1);
   atomicAdd(&sh[2 * g1 + 1], q1);
   __syncthreads();
-  if (threadIdx.x < GN_GROUPS * 2) atomicAdd(&sums[static_cast<long long>(n) * GN_GROUPS * 2 + threadIdx.x], sh[threadIdx.x]);
+  if (threadIdx.x < GN_GROUPS * 2)
+    part[(static_cast<long long>(n) * gridDim.x + blockIdx.x) * GN_GROUPS * 2 + threadIdx.x] = sh[threadIdx.x];
 }
 
-__device__ __forceinline__ void gn_mean_rstd(const float* __restrict__ sums, long long n, int g, float inv_cnt,
+// one warp per (image, group): lanes walk the tiles in a fixed order, then a shuffle tree -> deterministic
+__global__ void gn_finalize_kernel(const float* __restrict__ part, int total, int tiles, float inv_cnt,
+                                   float* __restrict__ mr) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= total) return;
+  const int n = w / GN_GROUPS, g = w - n * GN_GROUPS;
+  const float2* p = reinterpret_cast<const float2*>(part) + static_cast<long long>(n) * tiles * GN_GROUPS + g;
+  float s = 0.f, q = 0.f;
+  for (int t = lane; t < tiles; t += 32) {
+    const float2 v = p[static_cast<long long>(t) * GN_GROUPS];
+    s += v.x;
+    q += v.y;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    const float mean = s * inv_cnt;
+    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+    mr[2 * w] = mean;
+    mr[2 * w + 1] = rsqrtf(var + GN_EPS);
+  }
+}
+
+__device__ __forceinline__ void gn_mean_rstd(const float* __restrict__ mr, long long n, int g, float /*inv_cnt*/,
                                              float& mean, float& rstd) {
-  const float s = sums[(n * GN_GROUPS + g) * 2], q = sums[(n * GN_GROUPS + g) * 2 + 1];
-  mean = s * inv_cnt;
-  const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
-  rstd = rsqrtf(var + GN_EPS);
+  const float2 v = __ldg(reinterpret_cast<const float2*>(mr) + n * GN_GROUPS + g);
+  mean = v.x;
+  rstd = v.y;
 }
 
 __device__ __forceinline__ uint4 gn_apply8(const uint4 v, float m0, float r0, float m1, float r1,
@@ -147,22 +170,50 @@ __device__ __forceinline__ uint4 gn_apply8(const uint4 v, float m0, float r0, fl
   return make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
 }
 
+// grid (chunks, N); block 256; every thread owns a fixed channel octet (256 % (C/8) == 0), so the group
+// statistics and the affine parameters are loop invariant and the loop body is load / 8 FMA (+swish) / store.
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
-                const float* __restrict__ beta, long long total, int HW, int C, int do_swish, uint4* __restrict__ y) {
+gn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ mr, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int HW, int C, int do_swish, uint4* __restrict__ y) {
   const int C8 = C / 8;
   const int gch = C / GN_GROUPS;
-  const float inv_cnt = 1.0f / (static_cast<float>(HW) * static_cast<float>(gch));
-  const long long per_img = static_cast<long long>(HW) * C8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = i / per_img;
-    const int c8 = static_cast<int>(i % C8);
-    const int c0 = c8 * 8;
-    float m0, r0, m1, r1;
-    gn_mean_rstd(sums, n, c0 / gch, inv_cnt, m0, r0);
-    gn_mean_rstd(sums, n, (c0 + 4) / gch, inv_cnt, m1, r1);
-    y[i] = gn_apply8(__ldg(x + i), m0, r0, m1, r1, gamma, beta, c0, do_swish != 0);
+  const int n = blockIdx.y;
+  const int c8 = threadIdx.x % C8;
+  const int c0 = c8 * 8;
+  float m0, r0, m1, r1;
+  gn_mean_rstd(mr, n, c0 / gch, 0.f, m0, r0);
+  gn_mean_rstd(mr, n, (c0 + 4) / gch, 0.f, m1, r1);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+  const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+  const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+  // y = x * sc + sh
+  const float sc[8] = {r0 * ga.x, r0 * ga.y, r0 * ga.z, r0 * ga.w, r1 * gb.x, r1 * gb.y, r1 * gb.z, r1 * gb.w};
+  const float sh[8] = {ba.x - m0 * sc[0], ba.y - m0 * sc[1], ba.z - m0 * sc[2], ba.w - m0 * sc[3],
+                       bb.x - m1 * sc[4], bb.y - m1 * sc[5], bb.z - m1 * sc[6], bb.w - m1 * sc[7]};
+  const long long items = static_cast<long long>(HW) * C8;
+  const uint4* xn = x + static_cast<long long>(n) * items;
+  uint4* yn = y + static_cast<long long>(n) * items;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < items; i += 2 * stride) {
+    const bool two = i + stride < items;
+    const uint4 v0 = __ldg(xn + i);
+    uint4 v1 = make_uint4(0, 0, 0, 0);
+    if (two) v1 = __ldg(xn + i + stride);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const uint4 v = h ? v1 : v0;
+      const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+      float o[8] = {fmaf(a.x, sc[0], sh[0]), fmaf(a.y, sc[1], sh[1]), fmaf(b.x, sc[2], sh[2]), fmaf(b.y, sc[3], sh[3]),
+                    fmaf(c.x, sc[4], sh[4]), fmaf(c.y, sc[5], sh[5]), fmaf(d.x, sc[6], sh[6]), fmaf(d.y, sc[7], sh[7])};
+      if (do_swish) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = swish(o[e]);
+      }
+      yn[i + h * stride] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                      pack_bf16x2(o[6], o[7]));
+    }
   }
 }
 
@@ -459,26 +510,39 @@ int vqvae_nhwc_f32_to_nchw_f32(const float* in, int N, int C, int HW, float* out
   return MGV_OK;
 }
 
-int vqvae_gn_stats(const __nv_bfloat16* x, int N, int HW, int C, float* sums, cudaStream_t s) {
+int vqvae_gn_stats(const __nv_bfloat16* x, int N, int HW, int C, float* part, int* tiles_out, cudaStream_t s) {
   MGV_REQUIRE(C % GN_GROUPS == 0 && (C == 128 || C == 256 || C == 512), "gn_stats: C=%d unsupported", C);
-  if (N == 0) return MGV_OK;
   const long long items = static_cast<long long>(HW) * (C / 8);
   int chunks = static_cast<int>((items + 256 * 8 - 1) / (256 * 8));
-  const int cap = (num_sms() * 8 + N - 1) / N;
+  const int cap = (num_sms() * 8 + (N > 0 ? N : 1) - 1) / (N > 0 ? N : 1);
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
-  gn_stats_kernel<<<dim3(chunks, N), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), HW, C, sums);
+  if (tiles_out) *tiles_out = chunks;
+  if (N == 0) return MGV_OK;
+  gn_stats_kernel<<<dim3(chunks, N), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), HW, C, part);
   MGV_CHECK_CUDA(cudaGetLastError());
   return MGV_OK;
 }
 
-int vqvae_gn_apply(const __nv_bfloat16* x, const float* sums, const float* gamma, const float* beta, int N, int HW, int C,
+int vqvae_gn_finalize(const float* part, int N, int tiles, float count, float* mr, cudaStream_t s) {
+  if (N == 0) return MGV_OK;
+  const int total = N * GN_GROUPS;   // warps
+  gn_finalize_kernel<<<ceil_div(total * 32, 256), 256, 0, s>>>(part, total, tiles, 1.0f / count, mr);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
+int vqvae_gn_apply(const __nv_bfloat16* x, const float* mr, const float* gamma, const float* beta, int N, int HW, int C,
                    int do_swish, __nv_bfloat16* y, cudaStream_t s) {
   MGV_REQUIRE(C == 128 || C == 256 || C == 512, "gn_apply: C=%d unsupported", C);
-  const long long total = static_cast<long long>(N) * HW * (C / 8);
-  if (total == 0) return MGV_OK;
-  gn_apply_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), sums, gamma, beta, total, HW, C,
-                                                       do_swish, reinterpret_cast<uint4*>(y));
+  if (N == 0 || HW == 0) return MGV_OK;
+  const long long items = static_cast<long long>(HW) * (C / 8);
+  int chunks = static_cast<int>((items + 256 * 4 - 1) / (256 * 4));
+  const int cap = (num_sms() * 16 + N - 1) / N;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  gn_apply_kernel<<<dim3(chunks, N), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), mr, gamma, beta, HW, C, do_swish,
+                                                  reinterpret_cast<uint4*>(y));
   MGV_CHECK_CUDA(cudaGetLastError());
   return MGV_OK;
 }

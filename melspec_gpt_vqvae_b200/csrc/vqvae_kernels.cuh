@@ -20,10 +20,14 @@ int vqvae_gather_rows(const long long* idx, const __nv_bfloat16* table, long lon
 int vqvae_nchw_f32_to_nhwc_bf16(const float* in, int N, int C, int HW, __nv_bfloat16* out, cudaStream_t s);
 int vqvae_nhwc_f32_to_nchw_f32(const float* in, int N, int C, int HW, float* out, cudaStream_t s);
 
-// GroupNorm(32 groups, eps 1e-6): sums[n][g] = {sum, sumsq} over HW x (C/32) elements
-int vqvae_gn_stats(const __nv_bfloat16* x, int N, int HW, int C, float* sums /*pre-zeroed [N,32,2]*/, cudaStream_t s);
-// y = gn(x) * gamma + beta, optionally followed by swish (x * sigmoid(x))
-int vqvae_gn_apply(const __nv_bfloat16* x, const float* sums, const float* gamma, const float* beta, int N, int HW, int C,
+// GroupNorm(32 groups, eps 1e-6) statistics as per-tile partial sums: part[(n * tiles + tile) * 64 + g * 2 + {sum, sumsq}].
+// Producers: the conv epilogue (gemm_tc.cu, one slot per CTA) or vqvae_gn_stats (one slot per chunk; returns the
+// number of chunks per image in *tiles_out).  No atomics: the result is deterministic.
+int vqvae_gn_stats(const __nv_bfloat16* x, int N, int HW, int C, float* part, int* tiles_out, cudaStream_t s);
+// folds the tiles in a fixed order: mr[n][g] = {mean, rstd}; count = HW * C/32
+int vqvae_gn_finalize(const float* part, int N, int tiles, float count, float* mr /*[N,32,2]*/, cudaStream_t s);
+// y = gn(x) * gamma + beta, optionally followed by swish (x * sigmoid(x)); mr from vqvae_gn_finalize
+int vqvae_gn_apply(const __nv_bfloat16* x, const float* mr, const float* gamma, const float* beta, int N, int HW, int C,
                    int do_swish, __nv_bfloat16* y, cudaStream_t s);
 
 // nearest-neighbour 2x upsample (F.interpolate scale_factor=2 mode="nearest", :183)
@@ -33,7 +37,7 @@ int vqvae_upsample2x(const __nv_bfloat16* x, int N, int H, int W, int C, __nv_bf
 int vqvae_spatial_attention(const __nv_bfloat16* qkv, int N, int T, int C, __nv_bfloat16* o, cudaStream_t s);
 
 // Decoder tail (:389-391): out[n,0,y,x] = conv3x3(swish(gn(h)), w (1,C,3,3)) + b ; h NHWC bf16, out fp32
-int vqvae_norm_swish_conv_out(const __nv_bfloat16* h, const float* sums, const float* gamma, const float* beta,
+int vqvae_norm_swish_conv_out(const __nv_bfloat16* h, const float* mr, const float* gamma, const float* beta,
                               const float* w /*[9][C] fp32*/, const float* bias, int N, int H, int W, int C, float* out,
                               cudaStream_t s);
 

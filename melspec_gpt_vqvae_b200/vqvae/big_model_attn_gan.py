@@ -113,6 +113,10 @@ class VectorQuantizer(nn.Module):
         quantized = torch.empty_like(z)
         encodings = torch.empty(B * HW, K, dtype=torch.float32, device=dev)
         scalars = torch.zeros(2, dtype=torch.float32, device=dev)
+        if B * HW == 0:     # empty batch: mse / perplexity of nothing (the reference returns nan / 1.0)
+            scalars[0] = float("nan")
+            scalars[1] = 1.0
+            return scalars[0], quantized, (scalars[1], encodings, idx.unsqueeze(1))
         ws = torch.empty((8 + 4 * K + 7) // 8, dtype=torch.float64, device=dev)
         _lib.check(L.mgv_vq_finish(_lib.ptr(z), _lib.ptr(cb), _lib.ptr(idx), B, C, HW, K, float(self._commitment_cost),
                                    _lib.ptr(quantized), _lib.ptr(encodings), ctypes.c_void_p(scalars.data_ptr()),

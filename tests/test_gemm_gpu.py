@@ -50,6 +50,35 @@ def test_gemm_vs_simt_reference(M, N, K, bn, split, epi):
         assert (outs[0] - ref).abs().max().item() <= 1e-3 * scale
 
 
+@pytest.mark.parametrize("M,N,K,bn,split,epi", [
+    (3072, 64, 1024, 64, 8, 4), (1024, 64, 1024, 64, 16, 4), (4096, 64, 1024, 64, 4, 4), (1024, 64, 4096, 64, 16, 4),
+    (3072, 4, 1024, 32, 8, 4), (1024, 1, 1024, 32, 1, 3), (4096, 37, 1024, 64, 1, 1), (128, 200, 256, 256, 1, 2),
+    (1472, 64, 1472, 64, 1, 2),
+])
+def test_gemm_swapab_vs_torch(M, N, K, bn, split, epi):
+    """decode-step form: weights (M,K) are the 128-row operand, N batch rows the MMA N dim, output transposed."""
+    torch.manual_seed(M + N + K)
+    W = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    X = (torch.randn(N, K, device="cuda") * 0.5).bfloat16()
+    bias = torch.randn(M, device="cuda")
+    ref = X.float() @ W.float().t() + bias          # (N, M)
+    init = torch.randn(N, M, device="cuda")
+    if epi == 1:
+        out = torch.zeros(N, M, device="cuda", dtype=torch.bfloat16)
+        ref = torch.nn.functional.gelu(ref)
+    else:
+        out = init.clone()
+        if epi in (3, 4):
+            ref = ref + init
+    resid = out if epi == 3 else None
+    _lib.check(_lib.load().mgv_test_gemm_swapab(0, _lib.ptr(W), _lib.ptr(X), M, N, K, epi, _lib.ptr(bias), _lib.ptr(out),
+                                                _lib.ptr(resid), bn, split, S0))
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    tol = (1.0 / 128) * scale if epi == 1 else 1e-3 * scale
+    assert (out.float() - ref).abs().max().item() <= tol
+
+
 @pytest.mark.parametrize("n,H,W,Cin,Cout,stride,resid", [
     (2, 5, 53, 256, 512, 1, False), (2, 10, 106, 512, 512, 1, True), (1, 40, 424, 128, 128, 1, False),
     (1, 80, 848, 128, 128, 1, True), (2, 80, 848, 128, 128, 2, False), (2, 10, 106, 256, 256, 2, False),

@@ -49,7 +49,13 @@ def test_decode_batch_independence_and_oracle(model_and_sd):
     print("decode B=3 vs oracle: max %.4f rms %.4f" % (emax, erms))
     assert erms <= 0.035 and emax <= 0.2
     one = m.decode_codes(codes[1:2].cuda()).cpu()
-    assert float((one - mel[1:2]).abs().max()) <= 1e-2     # a clip's mel does not depend on its batch neighbours
+    # a clip's mel does not depend on its batch neighbours: every reduction (GroupNorm statistics included) is
+    # per image and deterministic, so the result is bit-identical
+    dmax, drms = err_stats(one, mel[1:2])
+    print("batch independence: max %.6f rms %.6f" % (dmax, drms))
+    assert dmax == 0.0
+    again = m.decode_codes(codes.cuda()).cpu()
+    assert torch.equal(again, mel), "decode is not deterministic run to run"
     with pytest.raises(RuntimeError):
         m.decode_codes(torch.full((1, 265), 128, dtype=torch.long, device="cuda"))
 
