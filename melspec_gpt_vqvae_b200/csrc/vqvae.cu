@@ -255,6 +255,8 @@ struct Ctx {
   }
 };
 
+int stats_of(struct Ctx& c, const __nv_bfloat16* x, int HW, int C, float* stats_out);
+
 int conv_stages() {
   static int v = -1;
   if (v < 0) {
@@ -279,10 +281,12 @@ int conv3(Ctx& c, const Conv& w, const __nv_bfloat16* x, int Hin, int Win, int s
   a.bias = w.b; a.out = out; a.resid = resid;
   a.bn = 128;
   a.max_stages = conv_stages();   // 2 stages = 64 KB -> three CTAs per SM: epilogues overlap the other CTAs' MMAs
-  if (stats_out) { a.gn_sum = c.v->gn_part; a.gn_group_ch = w.cout / 32; }
+  static const bool unfused = getenv("MGV_UNFUSED_GNSTATS") != nullptr;   // debugging aid
+  if (stats_out && !unfused) { a.gn_sum = c.v->gn_part; a.gn_group_ch = w.cout / 32; }
   a.stream = c.s;
   c.v->launches++;
   MGV_TRY(gemm_bf16_tc(a));
+  if (stats_out && unfused) return stats_of(c, out, a.H * a.W, w.cout, stats_out);
   if (stats_out) {
     // tiles per image of the conv kernel's grid (see fill_params in gemm_tc.cu)
     int wb = 16;

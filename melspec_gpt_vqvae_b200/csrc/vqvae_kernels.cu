@@ -87,9 +87,7 @@ __global__ void nhwc_to_nchw_f32_kernel(const float* __restrict__ in, int N, int
 // grid (chunks, N); block 256; every thread owns a fixed channel octet (256 % (C/8) == 0)
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const uint4* __restrict__ x, int HW, int C, float* __restrict__ part) {
-  __shared__ float sh[GN_GROUPS * 2];
-  if (threadIdx.x < GN_GROUPS * 2) sh[threadIdx.x] = 0.f;
-  __syncthreads();
+  __shared__ float4 sh[256];   // per-thread (sum0, sq0, sum1, sq1) of its two 4-channel halves
   const int C8 = C / 8;
   const int n = blockIdx.y;
   const long long items = static_cast<long long>(HW) * C8;
@@ -104,16 +102,21 @@ gn_stats_kernel(const uint4* __restrict__ x, int HW, int C, float* __restrict__ 
     s1 += (c.x + c.y) + (d.x + d.y);
     q1 += (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
   }
-  const int c8 = threadIdx.x % C8;
-  const int gch = C / GN_GROUPS;  // 4, 8, 16
-  const int g0 = (c8 * 8) / gch, g1 = (c8 * 8 + 4) / gch;
-  atomicAdd(&sh[2 * g0], s0);
-  atomicAdd(&sh[2 * g0 + 1], q0);
-  atomicAdd(&sh[2 * g1], s1);
-  atomicAdd(&sh[2 * g1 + 1], q1);
+  sh[threadIdx.x] = make_float4(s0, q0, s1, q1);
   __syncthreads();
-  if (threadIdx.x < GN_GROUPS * 2)
-    part[(static_cast<long long>(n) * gridDim.x + blockIdx.x) * GN_GROUPS * 2 + threadIdx.x] = sh[threadIdx.x];
+  // deterministic fold: thread (g, stat) walks the contributing threads in a fixed order (no atomics)
+  if (threadIdx.x < GN_GROUPS * 2) {
+    const int g = threadIdx.x >> 1, stat = threadIdx.x & 1;
+    const int gch = C / GN_GROUPS;  // 4, 8, 16 channels per group
+    float acc = 0.f;
+    for (int t = 0; t < 256; ++t) {
+      const int c0 = (t % C8) * 8;
+      const float4 v = sh[t];
+      if (c0 / gch == g) acc += stat ? v.y : v.x;
+      if ((c0 + 4) / gch == g) acc += stat ? v.w : v.z;
+    }
+    part[(static_cast<long long>(n) * gridDim.x + blockIdx.x) * GN_GROUPS * 2 + threadIdx.x] = acc;
+  }
 }
 
 // one warp per (image, group): lanes walk the tiles in a fixed order, then a shuffle tree -> deterministic
