@@ -546,6 +546,9 @@ int launch_tc(const GemmArgs& a, KParams& p) {
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // ask for the full shared-memory carve-out so that several CTAs (small rings) can share an SM
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   dim3 grid;

@@ -440,7 +440,7 @@ sample_step_kernel(const SampleArgs a) {
   unsigned int* done_counter = a.done_counter;
   pdl_launch_dependents();   // dependents may start their prologue / weight prefetch now
   pdl_wait();                // ... but our inputs need the upstream grid
-  extern __shared__ float sm_s[];
+  extern __shared__ __align__(16) float sm_s[];
   float* sx = sm_s;            // [C]
   float* sl = sx + a.C;        // [V]
   __shared__ float red[SAMPLE_THREADS / 32];
@@ -472,24 +472,37 @@ sample_step_kernel(const SampleArgs a) {
 
   // ---- head (no bias, minGPT.py:149,188) ; logits / temperature (:346)
   const int nchunk = a.C / 8;
-  for (int v = warp; v < a.V; v += SAMPLE_THREADS / 32) {
-    const uint4* wr = reinterpret_cast<const uint4*>(a.whead + static_cast<long long>(v) * a.C);
-    float acc = 0.f;
+  // 4 vocabulary rows per warp iteration: their weight loads are independent and all in flight together
+  for (int v0 = warp * 4; v0 < a.V; v0 += (SAMPLE_THREADS / 32) * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int ch = lane; ch < nchunk; ch += 32) {
-      const uint4 q = __ldg(wr + ch);
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      uint4 q[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 wf = unpack_bf16x2(w[e]);
-        acc = fmaf(sx[ch * 8 + 2 * e], wf.x, acc);
-        acc = fmaf(sx[ch * 8 + 2 * e + 1], wf.y, acc);
+      for (int r = 0; r < 4; ++r) {
+        q[r] = make_uint4(0, 0, 0, 0);
+        if (v0 + r < a.V) q[r] = __ldg(reinterpret_cast<const uint4*>(a.whead + static_cast<long long>(v0 + r) * a.C) + ch);
+      }
+      const float4 x0 = *reinterpret_cast<const float4*>(sx + ch * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(sx + ch * 8 + 4);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float2 w0 = unpack_bf16x2(q[r].x), w1 = unpack_bf16x2(q[r].y), w2 = unpack_bf16x2(q[r].z), w3 = unpack_bf16x2(q[r].w);
+        float t = acc[r];
+        t = fmaf(x0.x, w0.x, t); t = fmaf(x0.y, w0.y, t);
+        t = fmaf(x0.z, w1.x, t); t = fmaf(x0.w, w1.y, t);
+        t = fmaf(x1.x, w2.x, t); t = fmaf(x1.y, w2.y, t);
+        t = fmaf(x1.z, w3.x, t); t = fmaf(x1.w, w3.y, t);
+        acc[r] = t;
       }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float l = __fdiv_rn(acc, a.temperature);
-      sl[v] = l;
-      if (a.logits_out) a.logits_out[static_cast<long long>(b) * a.V + v] = l;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float tot = warp_sum(acc[r]);
+      if (lane == 0 && v0 + r < a.V) {
+        const float l = __fdiv_rn(tot, a.temperature);
+        sl[v0 + r] = l;
+        if (a.logits_out) a.logits_out[static_cast<long long>(b) * a.V + v0 + r] = l;
+      }
     }
   }
   __syncthreads();

@@ -97,11 +97,13 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ codebook
       cp_async_commit();
     };
 
-    float acc[8][8];
+    // packed fp32x2 accumulators (fma.rn.f32x2 = two independent IEEE fmas, bit-identical to scalar fmaf):
+    // acc2[ip][j] = dot products of vectors (2*ip, 2*ip+1) with code j
+    float2 acc2[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc2[i][j] = make_float2(0.f, 0.f);
     float xx_self = 0.f;  // |x|^2 of vector vg*8 + (cg & 7)
 
     issue_chunk(0, 0);
@@ -123,12 +125,15 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ codebook
         const float4 e0 = *reinterpret_cast<const float4*>(eb + k * VQ_MAX_K + cg * 8);
         const float4 e1 = *reinterpret_cast<const float4*>(eb + k * VQ_MAX_K + cg * 8 + 4);
         const float xself = xb[k * VQ_TILE_V + vg * 8 + (cg & 7)];
-        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const float2 xp[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y),
+                              make_float2(x1.z, x1.w)};
         const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) {
+          const float2 e2 = make_float2(ev[j], ev[j]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv[i], ev[j], acc[i][j]);
+          for (int ip = 0; ip < 4; ++ip) acc2[ip][j] = __ffma2_rn(xp[ip], e2, acc2[ip][j]);
+        }
         xx_self = fmaf(xself, xself, xx_self);
       }
       __syncthreads();  // everyone done with xs[buf] before it is refilled
@@ -147,7 +152,8 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ codebook
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int code = cg * 8 + j;
-        const float d = __fsub_rn(__fadd_rn(xx, eev[j]), __fmul_rn(2.0f, acc[i][j]));
+        const float dot = (i & 1) ? acc2[i >> 1][j].y : acc2[i >> 1][j].x;
+        const float d = __fsub_rn(__fadd_rn(xx, eev[j]), __fmul_rn(2.0f, dot));
         if (code < K && (d < best || bi == 0x7fffffff)) {  // strict <: first index wins inside the thread
           best = d;
           bi = code;

@@ -261,7 +261,7 @@ int conv_stages() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MGV_CONV_STAGES");
-    v = e ? atoi(e) : 2;
+    v = e ? atoi(e) : 3;
     if (v < 1) v = 1;
   }
   return v;
@@ -280,7 +280,7 @@ int conv3(Ctx& c, const Conv& w, const __nv_bfloat16* x, int Hin, int Win, int s
   a.epi = resid ? EPI_BF16_RESID : EPI_BF16;
   a.bias = w.b; a.out = out; a.resid = resid;
   a.bn = 128;
-  a.max_stages = conv_stages();   // 2 stages = 64 KB -> three CTAs per SM: epilogues overlap the other CTAs' MMAs
+  a.max_stages = conv_stages();   // 3 stages = 96 KB: two CTAs per SM, one's epilogue overlaps the other's MMAs
   static const bool unfused = getenv("MGV_UNFUSED_GNSTATS") != nullptr;   // debugging aid
   if (stats_out && !unfused) { a.gn_sum = c.v->gn_part; a.gn_group_ch = w.cout / 32; }
   a.stream = c.s;

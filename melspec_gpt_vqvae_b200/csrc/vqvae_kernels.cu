@@ -570,6 +570,8 @@ int vqvae_spatial_attention(const __nv_bfloat16* qkv, int N, int T, int C, __nv_
   static bool attr_set = false;
   if (!attr_set) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(spatial_attn_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(spatial_attn_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   MGV_REQUIRE(smem <= 200 * 1024, "spatial_attention: T=%d needs too much shared memory", T);
@@ -587,6 +589,8 @@ int vqvae_norm_swish_conv_out(const __nv_bfloat16* h, const float* sums, const f
   static bool attr_set = false;
   if (!attr_set) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(norm_swish_conv_out_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(norm_swish_conv_out_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   dim3 grid(ceil_div(W, CO_TW), ceil_div(H, CO_TH), N);

@@ -12,7 +12,8 @@ cfg = synthetic.GPT_VAS
 sd = synthetic.synthetic_gpt_state_dict(cfg, seed=783435, perturb=False)
 args = argparse.Namespace(embd_pdrop=0.5, resid_pdrop=0.5, attn_pdrop=0.5, reconstruct_spec="", device=dev, **cfg)
 lit = Lit_minGPT(args); lit.transformer.load_state_dict(sd, strict=False); lit = lit.eval().to(dev); lit.return_attention = False
-c = torch.randint(0, 8, (64, 1)).to(dev); x0 = torch.zeros(64, 0, dtype=torch.long, device=dev)
+t0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+c = torch.randint(0, 8, (64, 1)).to(dev); x0 = torch.randint(0, 128, (64, t0)).to(dev)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 lit.sample(x0, c, steps=steps, sample=True, top_k=100)
 torch.cuda.synchronize()
