@@ -98,118 +98,202 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 }
 
 // ------------------------------------------------------------------ prefill attention
-constexpr int AP_ROWS = 32;       // query rows per CTA
-constexpr int AP_THREADS = 128;
-constexpr int AP_KSTRIDE = 33;    // 32-bit words per K/V row in smem (64 bf16 + 1 pad word)
+// Causal (or prefix-unmasked) attention over a whole sequence, T <= 288, head dim 64, on the legacy tensor path
+// (mma.sync m16n8k16 bf16 -> fp32; this part is 4% of the prefill FLOPs, the GEMMs around it are tcgen05).
+// CTA = 4 warps = 64 query rows of one (sequence, head); K and V rows of the head are staged once in shared
+// memory (rows padded to 144 B: conflict-free fragment loads and ldmatrix).  Two passes over the key blocks:
+// pass 1 computes the exact row maximum and sum, pass 2 recomputes the scores, emits the normalised
+// probabilities (last layer only, fp32) and accumulates P V.  No [T,T] tensor ever reaches HBM except when the
+// caller asks for the attention map.
+constexpr int FA_BM = 64;
+constexpr int FA_BN = 64;
+constexpr int FA_LD = 72;          // bf16 elements per smem row (64 + 8 pad)
+constexpr int FA_THREADS = 128;
+constexpr int FA_MAXK = 320;       // >= GPT_MAX_T rounded up to FA_BN
 
-__global__ void __launch_bounds__(AP_THREADS)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r0), "=r"(r1)
+               : "r"(smem_u32(smem_row)));
+}
+
+__global__ void __launch_bounds__(FA_THREADS)
 attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T, int nh, int n_unmasked,
                     __nv_bfloat16* __restrict__ y, float* __restrict__ att, int att_T,
                     __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache, int Tmax) {
-  extern __shared__ uint32_t ap_smem[];
+  extern __shared__ __align__(16) __nv_bfloat16 fa_smem[];
+  __nv_bfloat16* sQ = fa_smem;                       // [64][72]
+  __nv_bfloat16* sK = sQ + FA_BM * FA_LD;            // [kpad][72]
   const int bh = blockIdx.y;
   const int b = bh / nh, h = bh - b * nh;
   const int C = nh * GPT_HEAD_DIM;
-  const int q0 = blockIdx.x * AP_ROWS;
-  const int q_end = min(q0 + AP_ROWS, T);
-  const int kmax = (q0 < n_unmasked) ? max(q_end, min(n_unmasked, T)) : q_end;
-  uint32_t* Ks = ap_smem;                                    // [kmax][33]
-  uint32_t* Vs = Ks + static_cast<size_t>(GPT_MAX_T) * AP_KSTRIDE;  // [kmax][33]
-  float* sq = reinterpret_cast<float*>(Vs + static_cast<size_t>(GPT_MAX_T) * AP_KSTRIDE);  // [4][64]
-  float* sp = sq + 4 * GPT_HEAD_DIM;                         // [4][GPT_MAX_T]
-
+  const int q0 = blockIdx.x * FA_BM;
+  const int q_end = min(q0 + FA_BM, T);
+  const int kmax = (q0 < n_unmasked) ? max(q_end, min(n_unmasked, T)) : q_end;   // keys any row of this block may see
+  const int nkb = (kmax + FA_BN - 1) / FA_BN;
+  const int kpad = nkb * FA_BN;
+  __nv_bfloat16* sV = sK + kpad * FA_LD;             // [kpad][72]
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const bool write_cache = (kcache != nullptr) && (blockIdx.x == gridDim.x - 1);  // last block sees every key
-  for (int i = t; i < kmax * 8; i += AP_THREADS) {
-    const int row = i >> 3, part = i & 7;
-    const __nv_bfloat16* base = qkv + (static_cast<long long>(b) * T + row) * (3 * C) + h * GPT_HEAD_DIM + part * 8;
-    const uint4 kq = *reinterpret_cast<const uint4*>(base + C);
-    const uint4 vq = *reinterpret_cast<const uint4*>(base + 2 * C);
-    uint32_t* kd = Ks + row * AP_KSTRIDE + part * 4;
-    uint32_t* vd = Vs + row * AP_KSTRIDE + part * 4;
-    kd[0] = kq.x; kd[1] = kq.y; kd[2] = kq.z; kd[3] = kq.w;
-    vd[0] = vq.x; vd[1] = vq.y; vd[2] = vq.z; vd[3] = vq.w;
-    if (write_cache) {
-      const long long co = ((static_cast<long long>(b) * nh + h) * Tmax + row) * GPT_HEAD_DIM + part * 8;
-      *reinterpret_cast<uint4*>(kcache + co) = kq;
-      *reinterpret_cast<uint4*>(vcache + co) = vq;
+
+  // ---- stage Q (this block's rows), K and V (rows < kmax; zero beyond) ; the last block also fills the KV cache
+  const bool write_cache = (kcache != nullptr) && (blockIdx.x == gridDim.x - 1);   // last block sees every key
+  for (int i = t; i < FA_BM * 8; i += FA_THREADS) {
+    const int r = i >> 3, part = i & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q0 + r < T)
+      v = *reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(b) * T + q0 + r) * (3 * C) + h * GPT_HEAD_DIM + part * 8);
+    *reinterpret_cast<uint4*>(sQ + r * FA_LD + part * 8) = v;
+  }
+  for (int i = t; i < kpad * 8; i += FA_THREADS) {
+    const int r = i >> 3, part = i & 7;
+    uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
+    if (r < kmax) {
+      const __nv_bfloat16* base = qkv + (static_cast<long long>(b) * T + r) * (3 * C) + h * GPT_HEAD_DIM + part * 8;
+      kq = *reinterpret_cast<const uint4*>(base + C);
+      vq = *reinterpret_cast<const uint4*>(base + 2 * C);
+      if (write_cache) {
+        const long long co = ((static_cast<long long>(b) * nh + h) * Tmax + r) * GPT_HEAD_DIM + part * 8;
+        *reinterpret_cast<uint4*>(kcache + co) = kq;
+        *reinterpret_cast<uint4*>(vcache + co) = vq;
+      }
     }
+    *reinterpret_cast<uint4*>(sK + r * FA_LD + part * 8) = kq;
+    *reinterpret_cast<uint4*>(sV + r * FA_LD + part * 8) = vq;
   }
   __syncthreads();
 
+  // ---- this warp's 16 query rows; thread owns rows (g, g+8) and column pairs 2*tq, 2*tq+1 of every 8-wide block
+  const int g = lane >> 2, tq = lane & 3;
+  const int rbase = q0 + warp * 16;
+  if (rbase >= T) return;                              // warp-uniform: nothing to do for a fully padded warp
+  const int row0 = min(rbase + g, T - 1), row1 = min(rbase + g + 8, T - 1);   // padded rows mirror the last row
+  uint32_t aq[4][4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const __nv_bfloat16* qa = sQ + (warp * 16 + g) * FA_LD + kk * 16 + tq * 2;
+    aq[kk][0] = *reinterpret_cast<const uint32_t*>(qa);
+    aq[kk][1] = *reinterpret_cast<const uint32_t*>(qa + 8 * FA_LD);
+    aq[kk][2] = *reinterpret_cast<const uint32_t*>(qa + 8);
+    aq[kk][3] = *reinterpret_cast<const uint32_t*>(qa + 8 * FA_LD + 8);
+  }
   const float scale = 1.0f / sqrtf(static_cast<float>(GPT_HEAD_DIM));   // minGPT.py:81
-  float* myq = sq + warp * GPT_HEAD_DIM;
-  float* myp = sp + warp * GPT_MAX_T;
-  const int nkb = (T + 31) / 32;
-  for (int r = warp; r < AP_ROWS; r += 4) {
-    const int row = q0 + r;
-    if (row >= T) break;
-    {
-      const uint32_t qw = *reinterpret_cast<const uint32_t*>(
-          qkv + (static_cast<long long>(b) * T + row) * (3 * C) + h * GPT_HEAD_DIM + 2 * lane);
-      const float2 qf = unpack_bf16x2(qw);
-      myq[2 * lane] = qf.x;
-      myq[2 * lane + 1] = qf.y;
-    }
-    __syncwarp();
-    float sc[GPT_MAX_T / 32];
-    float mx = -INFINITY;
+  // keys this warp's rows can see: causal limit of its last row, or the unmasked prefix
+  const int wlast = min(rbase + 15, T - 1);
+  const int wkmax = (rbase < n_unmasked) ? max(wlast + 1, min(n_unmasked, T)) : wlast + 1;
+  const int wnkb = (wkmax + FA_BN - 1) / FA_BN;
+
+  auto scores = [&](int jb, float (&sc)[8][4]) {
 #pragma unroll
-    for (int jj = 0; jj < GPT_MAX_T / 32; ++jj) {
-      sc[jj] = -INFINITY;
-      if (jj < nkb) {
-        const int key = jj * 32 + lane;
-        // mask[i][j] = tril, plus the unmasked prefix block (minGPT.py:65-68)
+    for (int nb = 0; nb < 8; ++nb) {
+      sc[nb][0] = sc[nb][1] = sc[nb][2] = sc[nb][3] = 0.f;
+      const __nv_bfloat16* kb = sK + (jb * FA_BN + nb * 8 + g) * FA_LD + tq * 2;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kb + kk * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kb + kk * 16 + 8);
+        mma_bf16_16816(sc[nb], aq[kk], b0, b1);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = jb * FA_BN + nb * 8 + tq * 2 + (e & 1);
+        const int row = (e < 2) ? row0 : row1;
+        // mask[i][j] = tril, plus the unmasked prefix block (minGPT.py:65-68, :82)
         const bool allowed = key < T && (key <= row || (row < n_unmasked && key < n_unmasked));
-        if (allowed) {
-          const uint32_t* kr = Ks + key * AP_KSTRIDE;
-          float s = 0.f;
-#pragma unroll 8
-          for (int d2 = 0; d2 < 32; ++d2) {
-            const float2 kf = unpack_bf16x2(kr[d2]);
-            s = fmaf(myq[2 * d2], kf.x, s);
-            s = fmaf(myq[2 * d2 + 1], kf.y, s);
-          }
-          sc[jj] = s * scale;
-        }
-        mx = fmaxf(mx, sc[jj]);
+        sc[nb][e] = allowed ? sc[nb][e] * scale : -INFINITY;
       }
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
+  };
+
+  // ---- pass 1: exact row max and sum
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int jb = 0; jb < wnkb; ++jb) {
+    float sc[8][4];
+    scores(jb, sc);
+    float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < GPT_MAX_T / 32; ++jj) {
-      if (jj < nkb) {
-        sc[jj] = (sc[jj] == -INFINITY) ? 0.f : expf(sc[jj] - mx);
-        sum += sc[jj];
-      }
+    for (int nb = 0; nb < 8; ++nb) {
+      bm0 = fmaxf(bm0, fmaxf(sc[nb][0], sc[nb][1]));
+      bm1 = fmaxf(bm1, fmaxf(sc[nb][2], sc[nb][3]));
     }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    float* arow = (att && row < att_T) ? att + ((static_cast<long long>(b) * nh + h) * att_T + row) * att_T : nullptr;
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);   // key 0 is always allowed -> finite from block 0 on
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < GPT_MAX_T / 32; ++jj) {
-      if (jj < nkb) {
-        const int key = jj * 32 + lane;
-        const float p = sc[jj] * inv;
-        if (key < T) {
-          myp[key] = p;
-          if (arow && key < att_T && sc[jj] != 0.f) arow[key] = p;
-        }
+    for (int nb = 0; nb < 8; ++nb) {
+      s0 += expf(sc[nb][0] - n0) + expf(sc[nb][1] - n0);
+      s1 += expf(sc[nb][2] - n1) + expf(sc[nb][3] - n1);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    l0 = l0 * expf(m0 - n0) + s0;
+    l1 = l1 * expf(m1 - n1) + s1;
+    m0 = n0;
+    m1 = n1;
+  }
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+
+  // ---- pass 2: probabilities (+ optional attention map) and O = P V
+  float o[8][4];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+  const bool r0_ok = rbase + g < T, r1_ok = rbase + g + 8 < T;
+  float* arow0 = (att && r0_ok && row0 < att_T) ? att + ((static_cast<long long>(b) * nh + h) * att_T + row0) * att_T : nullptr;
+  float* arow1 = (att && r1_ok && row1 < att_T) ? att + ((static_cast<long long>(b) * nh + h) * att_T + row1) * att_T : nullptr;
+  for (int jb = 0; jb < wnkb; ++jb) {
+    float sc[8][4];
+    scores(jb, sc);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      sc[nb][0] = expf(sc[nb][0] - m0) * inv0;
+      sc[nb][1] = expf(sc[nb][1] - m0) * inv0;
+      sc[nb][2] = expf(sc[nb][2] - m1) * inv1;
+      sc[nb][3] = expf(sc[nb][3] - m1) * inv1;
+      const int key = jb * FA_BN + nb * 8 + tq * 2;
+      if (arow0) {   // buffer is pre-zeroed: write only non-zero probabilities
+        if (key < att_T && sc[nb][0] != 0.f) arow0[key] = sc[nb][0];
+        if (key + 1 < att_T && sc[nb][1] != 0.f) arow0[key + 1] = sc[nb][1];
+      }
+      if (arow1) {
+        if (key < att_T && sc[nb][2] != 0.f) arow1[key] = sc[nb][2];
+        if (key + 1 < att_T && sc[nb][3] != 0.f) arow1[key + 1] = sc[nb][3];
       }
     }
-    __syncwarp();
-    const int kend = (row < n_unmasked) ? max(row + 1, min(n_unmasked, T)) : row + 1;
-    float a0 = 0.f, a1 = 0.f;
-    for (int key = 0; key < kend; ++key) {
-      const float p = myp[key];
-      const float2 vf = unpack_bf16x2(Vs[key * AP_KSTRIDE + lane]);
-      a0 = fmaf(p, vf.x, a0);
-      a1 = fmaf(p, vf.y, a1);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {     // 16 keys per step
+      uint32_t ap[4];
+      ap[0] = pack_bf16x2(sc[2 * ks][0], sc[2 * ks][1]);
+      ap[1] = pack_bf16x2(sc[2 * ks][2], sc[2 * ks][3]);
+      ap[2] = pack_bf16x2(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
+      ap[3] = pack_bf16x2(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
+      const __nv_bfloat16* vrow = sV + (jb * FA_BN + ks * 16 + (lane & 15)) * FA_LD;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, vrow + nd * 8);
+        mma_bf16_16816(o[nd], ap, b0, b1);
+      }
     }
-    *reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b) * T + row) * C + h * GPT_HEAD_DIM + 2 * lane) =
-        pack_bf16x2(a0, a1);
-    __syncwarp();
+  }
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) {
+    const int dim = nd * 8 + tq * 2;
+    if (r0_ok)
+      *reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b) * T + rbase + g) * C + h * GPT_HEAD_DIM + dim) =
+          pack_bf16x2(o[nd][0], o[nd][1]);
+    if (r1_ok)
+      *reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b) * T + rbase + g + 8) * C + h * GPT_HEAD_DIM + dim) =
+          pack_bf16x2(o[nd][2], o[nd][3]);
   }
 }
 
@@ -618,14 +702,18 @@ int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_
                           int att_T, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int Tmax, cudaStream_t s) {
   MGV_REQUIRE(T >= 1 && T <= GPT_MAX_T, "attention: T=%d exceeds %d", T, GPT_MAX_T);
   if (B == 0) return MGV_OK;
-  const size_t smem = (2 * static_cast<size_t>(GPT_MAX_T) * AP_KSTRIDE) * 4 + (4 * GPT_HEAD_DIM + 4 * GPT_MAX_T) * 4;
+  const int kpad = ceil_div(T, FA_BN) * FA_BN;
+  const size_t smem = static_cast<size_t>(FA_BM + 2 * kpad) * FA_LD * sizeof(__nv_bfloat16);
   static bool attr_set = false;
   if (!attr_set) {
-    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (FA_BM + 2 * FA_MAXK) * FA_LD * 2));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  dim3 grid(ceil_div(T, AP_ROWS), B * nh);
-  attn_prefill_kernel<<<grid, AP_THREADS, smem, s>>>(qkv, B, T, nh, n_unmasked, y, att, att_T, kcache, vcache, Tmax);
+  dim3 grid(ceil_div(T, FA_BM), B * nh);
+  attn_prefill_kernel<<<grid, FA_THREADS, smem, s>>>(qkv, B, T, nh, n_unmasked, y, att, att_T, kcache, vcache, Tmax);
   MGV_CHECK_CUDA(cudaGetLastError());
   return MGV_OK;
 }
