@@ -263,7 +263,7 @@ def cpu_reference_rate(threads, budget_s):
     ocfg = gpt_oracle.GPTCfg(**cfg)
     sd = synthetic.synthetic_gpt_state_dict(cfg, seed=SEED, perturb=False)
     g = torch.Generator().manual_seed(SEED)
-    bs = 2
+    bs = 8    # the reference would batch the 64 clips; 8 keeps the sample bounded while giving the CPU GEMMs real batches
     c = torch.randint(0, cfg["class_size"], (bs, 1), generator=g)
     # the reference recomputes the full forward at every step: cost(n) for context n; sample a few n
     ctxs = [0, 66, 132, 198, 264]

@@ -40,8 +40,6 @@ struct KParams {
   int gn_group_ch;
   int evict_first_w;   // L2 evict-first hint on the weight operand
   int transpose_out;   // swap-AB: weights are the A operand, output written transposed
-  int* split_counters; // split-K finisher ticket counters (per feature tile) or null
-  void* finish_out;    // bf16 gelu(acc) written by the last split CTA
 };
 
 template <int BN>
@@ -236,43 +234,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               default: static_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(v); break;
             }
           }
-        }
-      }
-      if (p.split_counters != nullptr) {
-        // "last block" pattern: publish our reductions, take a ticket; the CTA that draws the last ticket of
-        // this feature tile sees every split's contribution and finishes the tile (GELU -> bf16, clear acc).
-        uint32_t* s_ticket = tmem_slot + 1;
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) {
-          const int tile = blockIdx.x * gridDim.y + blockIdx.y;
-          *s_ticket = static_cast<uint32_t>(atomicAdd(p.split_counters + tile, 1));
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (*s_ticket == gridDim.z - 1) {
-          __threadfence();
-          if (feat_ok) {
-            float* acc32 = static_cast<float*>(p.out);
-            __nv_bfloat16* fo = static_cast<__nv_bfloat16*>(p.finish_out);
-            const int bend = (n0 + BN < p.N) ? n0 + BN : p.N;
-            // 8 independent L2 loads in flight per thread (lanes = consecutive features: coalesced rows)
-#pragma unroll 1
-            for (int b0 = n0; b0 < bend; b0 += 8) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                v[i] = (b0 + i < bend) ? __ldcg(acc32 + static_cast<long long>(b0 + i) * p.ldo + feat) : 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (b0 + i < bend) {
-                  const long long o = static_cast<long long>(b0 + i) * p.ldo + feat;
-                  fo[o] = __float2bfloat16(gelu_erf(v[i]));
-                  acc32[o] = 0.f;
-                }
-              }
-            }
-          }
-          if (threadIdx.x == 64) p.split_counters[blockIdx.x * gridDim.y + blockIdx.y] = 0;
         }
       }
     } else
@@ -490,11 +451,7 @@ int fill_params(const GemmArgs& a, KParams& p) {
   p.a_mode = a.a_mode;
   p.evict_first_w = a.weights_evict_first ? 1 : 0;
   p.transpose_out = a.transpose_out ? 1 : 0;
-  p.split_counters = a.split_counters;
-  p.finish_out = a.finish_out;
-  if (a.split_counters) {
-    MGV_REQUIRE(a.transpose_out && a.epi == EPI_F32_ATOMIC && a.finish_out, "gemm: split-K finisher needs transpose_out + EPI_F32_ATOMIC");
-  }
+
   p.gn_sum = a.gn_sum;
   p.gn_group_ch = a.gn_group_ch;
   if (a.gn_sum) {

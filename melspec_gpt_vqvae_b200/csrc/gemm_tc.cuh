@@ -55,11 +55,6 @@ struct GemmArgs {
   // accumulator tile is written TRANSPOSED: out[n * ldo + m] (ldo defaults to M), bias is per m.
   // N need not be a multiple of 32 (TMA zero-fills the missing activation rows).
   bool transpose_out = false;
-  // split-K finisher (transpose_out + EPI_F32_ATOMIC): the last split CTA of a feature tile (ticket from
-  // split_counters[tile], zero-initialised, self-resetting) reads the reduced tile back, writes
-  // finish_out = bf16(gelu_erf(acc)) and clears the accumulator for its next use.
-  int* split_counters = nullptr;
-  void* finish_out = nullptr;
   // launch
   bool pdl = false;
   bool weights_evict_first = false;  // L2 evict-first hint on the weight operand (B, or A when transpose_out)

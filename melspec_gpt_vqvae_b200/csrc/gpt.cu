@@ -68,7 +68,6 @@ struct Gpt {
   float *dx = nullptr, *dqkv32 = nullptr, *dh32 = nullptr;
   __nv_bfloat16 *dln = nullptr, *dy = nullptr, *dh = nullptr, *kv = nullptr;
   int* d_state = nullptr;  // [0]=pos, [1]=done counter, [2]=err flag
-  int* d_counters = nullptr;  // split-K finisher tickets (zero-initialised, self-resetting)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   bool pdl = false;
@@ -258,8 +257,6 @@ int gpt_create(const GptConfig* cfg, Gpt** out) {
   g->loaded.assign(g->n_tensors, 0);
   cudaMalloc(&g->d_state, 4 * sizeof(int));
   cudaMemset(g->d_state, 0, 4 * sizeof(int));
-  cudaMalloc(&g->d_counters, 1024 * sizeof(int));
-  cudaMemset(g->d_counters, 0, 1024 * sizeof(int));
   cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&g->ev_in, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&g->ev_out, cudaEventDisableTiming);
@@ -288,7 +285,6 @@ int gpt_destroy(Gpt* g) {
   cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
   cudaFree(g->kv);
   cudaFree(g->d_state);
-  cudaFree(g->d_counters);
   if (g->stream) cudaStreamDestroy(g->stream);
   if (g->ev_in) cudaEventDestroy(g->ev_in);
   if (g->ev_out) cudaEventDestroy(g->ev_out);
@@ -400,8 +396,7 @@ int gpt_forward(Gpt* g, const long long* idx, int B, int t, const float* prefix_
 namespace {
 
 int decode_gemm(Gpt* g, const __nv_bfloat16* X, const __nv_bfloat16* W, const float* bias, int B, int N, int K,
-                int split, int epi_direct, void* out, const void* resid, cudaStream_t s,
-                __nv_bfloat16* gelu_out = nullptr) {
+                int split, int epi_direct, void* out, const void* resid, cudaStream_t s) {
   // swap-AB: the weights are the 128-row MMA operand, the B batch rows are the MMA N dimension
   GemmArgs a;
   a.stream = s;
@@ -415,10 +410,6 @@ int decode_gemm(Gpt* g, const __nv_bfloat16* X, const __nv_bfloat16* W, const fl
   if (split > 1) {
     a.epi = EPI_F32_ATOMIC;
     a.split_k = split;
-    if (gelu_out) {   // last split CTA of each feature tile applies GELU and emits the bf16 operand of FC2
-      a.split_counters = g->d_counters;
-      a.finish_out = gelu_out;
-    }
   } else {
     a.epi = epi_direct;
     a.resid = resid;
@@ -441,6 +432,8 @@ int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int
     MGV_TRY(decode_gemm(g, g->dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, g->dx, g->dx, s));
     MGV_TRY(gpt_layernorm(g->dx, w.ln2_w, w.ln2_b, B, C, g->dln, nullptr, 0, s, g->pdl));
     if (fs) {
+      // (a "last split CTA applies GELU" finisher inside the FC1 kernel was measured slower than this tiny
+      //  elementwise kernel: 1287 vs 1111 us per position)
       MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_split, EPI_F32, g->dh32, nullptr, s));
       MGV_TRY(gpt_gelu_bf16(g->dh32, static_cast<long long>(B) * 4 * C, g->dh, true, s, g->pdl));
       g->launches += 1;
