@@ -42,7 +42,9 @@ struct KParams {
   int transpose_out;   // swap-AB: weights are the A operand, output written transposed
 };
 
-template <int BN>
+// DECODE = true: the swap-AB weight-streaming form only (plain A operand, transposed epilogue) -- the decode
+// loop launches this kernel ~100 times per position for a few microseconds each, so its code is kept minimal.
+template <int BN, bool DECODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const KParams p) {
@@ -68,7 +70,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (nkb > p.kb_per_split) nkb = p.kb_per_split;
 
   int m0 = 0, img = 0, x0 = 0, y0 = 0;
-  if (p.a_mode == A_PLAIN) {
+  if (DECODE || p.a_mode == A_PLAIN) {
     m0 = blockIdx.x * BM;
   } else {
     int t = blockIdx.x;
@@ -80,7 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     y0 = ty * p.hb;
   }
 
-  if (threadIdx.x >= 64) {   // 128 epilogue threads clear their warp's 64 bins
+  if (!DECODE && threadIdx.x >= 64) {   // 128 epilogue threads clear their warp's 64 bins
     s_bins[threadIdx.x - 64] = 0.f;
     s_bins[threadIdx.x + 64] = 0.f;
   }
@@ -110,12 +112,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =========================== TMA producer ===========================
     if (lane == 0) {
       const uint64_t hint_w = p.evict_first_w ? kEvictFirst : kEvictNormal;
-      const uint64_t hint_b = p.transpose_out ? kEvictNormal : hint_w;
-      const uint64_t hint_a = p.transpose_out ? hint_w : kEvictNormal;
-      const int cblocks = (p.a_mode == A_PLAIN) ? 1 : (p.Cin / BK);
+      const bool swap_ab = DECODE || p.transpose_out;
+      const uint64_t hint_b = swap_ab ? kEvictNormal : hint_w;
+      const uint64_t hint_a = swap_ab ? hint_w : kEvictNormal;
+      const int cblocks = (DECODE || p.a_mode == A_PLAIN) ? 1 : (p.Cin / BK);
       auto load_a = [&](int kb, int s) {
         uint8_t* dst = smem + s * STAGE_BYTES;
-        if (p.a_mode == A_PLAIN) {
+        if (DECODE || p.a_mode == A_PLAIN) {
           tma_load_2d(dst, &tmA, &full_bar[s], (kb0 + kb) * BK, m0, hint_a);
         } else {
           const int kk = kb0 + kb;
@@ -135,11 +138,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int pre = nkb < stages ? nkb : stages;
       for (int kb = 0; kb < pre; ++kb) {  // weights first: they do not depend on the upstream grid
         mbar_arrive_expect_tx(&full_bar[kb], STAGE_BYTES);
-        if (p.transpose_out) load_a(kb, kb); else load_b(kb, kb);
+        if (swap_ab) load_a(kb, kb); else load_b(kb, kb);
       }
       pdl_wait();
       for (int kb = 0; kb < pre; ++kb) {
-        if (p.transpose_out) load_b(kb, kb); else load_a(kb, kb);
+        if (swap_ab) load_b(kb, kb); else load_a(kb, kb);
       }
       for (int kb = pre; kb < nkb; ++kb) {
         const int s = kb % stages;
@@ -178,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int r_local = quarter * 32 + lane;
     bool row_ok;
     long long out_row;  // element offset of this thread's output row
-    if (p.a_mode == A_PLAIN) {
+    if (DECODE || p.a_mode == A_PLAIN) {
       const int row = m0 + r_local;
       row_ok = row < p.M;
       out_row = static_cast<long long>(row) * p.ldo;
@@ -191,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const bool add_bias = p.bias != nullptr && (p.epi != EPI_F32_ATOMIC || blockIdx.z == 0);
-    if (p.transpose_out) {
+    if (DECODE || p.transpose_out) {
       // swap-AB: this thread owns output feature `feat`; accumulator columns are batch rows.  For a fixed
       // batch row the 32 lanes of a warp touch 32 consecutive features: coalesced stores / reductions.
       const int feat = m0 + r_local;
@@ -236,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-    } else
+    } else if constexpr (!DECODE) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int col0 = n0 + c * 32;
@@ -370,7 +373,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    if (p.gn_sum != nullptr) {
+    }  // !DECODE
+    if (!DECODE && p.gn_sum != nullptr) {
       // one plain store per CTA and bin into this tile's slot (deterministic; folded by vqvae_gn_finalize)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int nbins = (BN / p.gn_group_ch) * 2;
@@ -479,7 +483,7 @@ int fill_params(const GemmArgs& a, KParams& p) {
   return MGV_OK;
 }
 
-template <int BN>
+template <int BN, bool DECODE>
 int launch_tc(const GemmArgs& a, KParams& p) {
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
   const int total_kb = a.K / BK;
@@ -502,9 +506,9 @@ int launch_tc(const GemmArgs& a, KParams& p) {
 
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, DECODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // ask for the full shared-memory carve-out so that several CTAs (small rings) can share an SM
-    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, DECODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
@@ -514,7 +518,7 @@ int launch_tc(const GemmArgs& a, KParams& p) {
   else
     grid = dim3(p.tiles_x * p.tiles_y * a.n_img, ceil_div(a.N, BN), 1);
   LaunchCfg lc(grid, dim3(GEMM_THREADS), smem, a.stream, a.pdl);
-  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN>, tmA, tmB, p));
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN, DECODE>, tmA, tmB, p));
   return MGV_OK;
 }
 
@@ -524,11 +528,20 @@ int gemm_bf16_tc(const GemmArgs& a) {
   KParams p;
   MGV_TRY(fill_params(a, p));
   if (a.a_mode == A_CONV3x3) MGV_REQUIRE(a.split_k == 1, "conv: split_k unsupported");
+  if (a.transpose_out) {   // decode form: compact kernel
+    switch (a.bn) {
+      case 32: return launch_tc<32, true>(a, p);
+      case 64: return launch_tc<64, true>(a, p);
+      case 128: return launch_tc<128, true>(a, p);
+      case 256: return launch_tc<256, true>(a, p);
+      default: set_error("gemm: bn=%d not in {32,64,128,256}", a.bn); return MGV_ERR_INVALID;
+    }
+  }
   switch (a.bn) {
-    case 32: return launch_tc<32>(a, p);
-    case 64: return launch_tc<64>(a, p);
-    case 128: return launch_tc<128>(a, p);
-    case 256: return launch_tc<256>(a, p);
+    case 32: return launch_tc<32, false>(a, p);
+    case 64: return launch_tc<64, false>(a, p);
+    case 128: return launch_tc<128, false>(a, p);
+    case 256: return launch_tc<256, false>(a, p);
     default: set_error("gemm: bn=%d not in {32,64,128,256}", a.bn); return MGV_ERR_INVALID;
   }
 }

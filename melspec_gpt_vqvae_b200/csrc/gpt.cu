@@ -47,6 +47,7 @@ struct DecodeTiles {
   int proj_split = 16;  //  8 row tiles x 16 = 128 CTAs
   int fc1_split = 4;    // 32 row tiles x 4  = 128 CTAs
   int fc2_split = 16;   //  8 row tiles x 16 = 128 CTAs
+  int head_split = 16;  //  1 row tile  x 16 (vocab 128)
 };
 
 struct Gpt {
@@ -65,7 +66,7 @@ struct Gpt {
   float* x = nullptr;
   __nv_bfloat16 *ln = nullptr, *qkv = nullptr, *y = nullptr, *h = nullptr;
   int dec_B = 0;  // decode batch capacity
-  float *dx = nullptr, *dqkv32 = nullptr, *dh32 = nullptr;
+  float *dx = nullptr, *dqkv32 = nullptr, *dh32 = nullptr, *dlogits = nullptr;
   __nv_bfloat16 *dln = nullptr, *dy = nullptr, *dh = nullptr, *kv = nullptr;
   int* d_state = nullptr;  // [0]=pos, [1]=done counter, [2]=err flag
   cudaStream_t stream = nullptr;
@@ -143,14 +144,15 @@ int ensure_prefill_ws(Gpt* g, int rows) {
 int ensure_decode_ws(Gpt* g, int B) {
   if (B <= g->dec_B) return MGV_OK;
   cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
-  cudaFree(g->kv);
-  g->dx = g->dqkv32 = g->dh32 = nullptr;
+  cudaFree(g->kv); cudaFree(g->dlogits);
+  g->dx = g->dqkv32 = g->dh32 = g->dlogits = nullptr;
   g->dln = g->dy = g->dh = g->kv = nullptr;
   g->dec_B = 0;
   const size_t C = g->C, R = B;
   MGV_CHECK_CUDA(cudaMalloc(&g->dx, R * C * 4));
   MGV_CHECK_CUDA(cudaMalloc(&g->dqkv32, R * 3 * C * 4));
   MGV_CHECK_CUDA(cudaMalloc(&g->dh32, R * 4 * C * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&g->dlogits, R * static_cast<size_t>(g->Vout) * 4));
   MGV_CHECK_CUDA(cudaMalloc(&g->dln, R * C * 2));
   MGV_CHECK_CUDA(cudaMalloc(&g->dy, R * C * 2));
   MGV_CHECK_CUDA(cudaMalloc(&g->dh, R * 4 * C * 2));
@@ -283,7 +285,7 @@ int gpt_destroy(Gpt* g) {
   cudaFree(g->slab);
   cudaFree(g->x); cudaFree(g->ln); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->h);
   cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
-  cudaFree(g->kv);
+  cudaFree(g->kv); cudaFree(g->dlogits);
   cudaFree(g->d_state);
   if (g->stream) cudaStreamDestroy(g->stream);
   if (g->ev_in) cudaEventDestroy(g->ev_in);
@@ -443,8 +445,11 @@ int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int
     MGV_TRY(decode_gemm(g, g->dh, w.wfc2, w.bfc2, B, C, 4 * C, tl.fc2_split, EPI_F32_RESID, g->dx, g->dx, s));
     g->launches += 3;
   }
+  // ln_f + head (minGPT.py:186-188) with the same kernels as the blocks, then the fused sampler
+  MGV_TRY(gpt_layernorm(g->dx, g->lnf_w, g->lnf_b, B, C, g->dln, nullptr, 0, s, g->pdl));
+  MGV_TRY(decode_gemm(g, g->dln, g->whead, nullptr, B, g->V, C, tl.head_split, EPI_F32, g->dlogits, nullptr, s));
   MGV_TRY(gpt_sample_step(sa, s, g->pdl));
-  g->launches += 1;
+  g->launches += 2;
   return MGV_OK;
 }
 
@@ -502,12 +507,13 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   // split-K accumulators start at zero; afterwards their consumers clear them for the next layer / position
   MGV_CHECK_CUDA(cudaMemsetAsync(g->dqkv32, 0, static_cast<size_t>(B) * 3 * g->C * 4, s));
   MGV_CHECK_CUDA(cudaMemsetAsync(g->dh32, 0, static_cast<size_t>(B) * 4 * g->C * 4, s));
+  MGV_CHECK_CUDA(cudaMemsetAsync(g->dlogits, 0, static_cast<size_t>(B) * g->Vout * 4, s));
   const int init_state[2] = {T0 - 1, 0};
   MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state, init_state, 2 * sizeof(int), cudaMemcpyHostToDevice, s));
 
   SampleArgs sa;
   memset(&sa, 0, sizeof(sa));
-  sa.x = g->dx; sa.lnf_w = g->lnf_w; sa.lnf_b = g->lnf_b; sa.whead = g->whead;
+  sa.logits_acc = g->dlogits;
   sa.B = B; sa.C = g->C; sa.V = g->V;
   sa.temperature = temperature; sa.top_k = top_k; sa.do_sample = do_sample; sa.seed = seed;
   sa.pos_ptr = g->d_state;

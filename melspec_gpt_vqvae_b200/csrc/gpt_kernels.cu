@@ -505,7 +505,7 @@ __device__ float philox_uniform(unsigned long long seed, uint32_t ctr0, uint32_t
   return static_cast<float>(c[0] >> 8) * (1.0f / 16777216.0f);
 }
 
-constexpr int SAMPLE_THREADS = 256;
+constexpr int SAMPLE_THREADS = 128;
 constexpr int SAMPLE_MAX_V = 1024;
 
 __device__ float block_reduce(float v, float* red, bool is_max) {
@@ -519,75 +519,29 @@ __device__ float block_reduce(float v, float* red, bool is_max) {
   return r;
 }
 
+// One CTA per sequence.  The logits of this position come from the head GEMM (ln_f and head run as the same
+// LayerNorm / tcgen05 kernels as the blocks); here: temperature, top-k threshold (ties kept), softmax,
+// multinomial / argmax, token append, embedding of the next position, position advance.
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_step_kernel(const SampleArgs a) {
   unsigned int* done_counter = a.done_counter;
-  pdl_launch_dependents();   // dependents may start their prologue / weight prefetch now
-  pdl_wait();                // ... but our inputs need the upstream grid
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float sm_s[];
-  float* sx = sm_s;            // [C]
-  float* sl = sx + a.C;        // [V]
+  float* sl = sm_s;            // [V]
   __shared__ float red[SAMPLE_THREADS / 32];
   __shared__ int s_tok;
   const int b = blockIdx.x;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int t = threadIdx.x, lane = t & 31;
   const int pos = *a.pos_ptr;
 
-  // ---- ln_f (minGPT.py:186)
-  const float* xr = a.x + static_cast<long long>(b) * a.C;
-  float s = 0.f;
-  for (int i = t; i < a.C; i += SAMPLE_THREADS) {
-    const float v = xr[i];
-    sx[i] = v;
-    s += v;
-  }
-  const float mean = block_reduce(s, red, false) / static_cast<float>(a.C);
-  float ssq = 0.f;
-  for (int i = t; i < a.C; i += SAMPLE_THREADS) {
-    const float d = sx[i] - mean;
-    ssq += d * d;
-  }
-  const float rstd = rsqrtf(block_reduce(ssq, red, false) / static_cast<float>(a.C) + 1e-5f);
-  for (int i = t; i < a.C; i += SAMPLE_THREADS) {
-    // rounded to bf16 like the prefill path, which feeds the head GEMM with bf16 activations
-    sx[i] = __bfloat162float(__float2bfloat16((sx[i] - mean) * rstd * __ldg(a.lnf_w + i) + __ldg(a.lnf_b + i)));
-  }
-  __syncthreads();
-
-  // ---- head (no bias, minGPT.py:149,188) ; logits / temperature (:346)
-  const int nchunk = a.C / 8;
-  // 4 vocabulary rows per warp iteration: their weight loads are independent and all in flight together
-  for (int v0 = warp * 4; v0 < a.V; v0 += (SAMPLE_THREADS / 32) * 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ch = lane; ch < nchunk; ch += 32) {
-      uint4 q[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        q[r] = make_uint4(0, 0, 0, 0);
-        if (v0 + r < a.V) q[r] = __ldg(reinterpret_cast<const uint4*>(a.whead + static_cast<long long>(v0 + r) * a.C) + ch);
-      }
-      const float4 x0 = *reinterpret_cast<const float4*>(sx + ch * 8);
-      const float4 x1 = *reinterpret_cast<const float4*>(sx + ch * 8 + 4);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float2 w0 = unpack_bf16x2(q[r].x), w1 = unpack_bf16x2(q[r].y), w2 = unpack_bf16x2(q[r].z), w3 = unpack_bf16x2(q[r].w);
-        float t = acc[r];
-        t = fmaf(x0.x, w0.x, t); t = fmaf(x0.y, w0.y, t);
-        t = fmaf(x0.z, w1.x, t); t = fmaf(x0.w, w1.y, t);
-        t = fmaf(x1.x, w2.x, t); t = fmaf(x1.y, w2.y, t);
-        t = fmaf(x1.z, w3.x, t); t = fmaf(x1.w, w3.y, t);
-        acc[r] = t;
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float tot = warp_sum(acc[r]);
-      if (lane == 0 && v0 + r < a.V) {
-        const float l = __fdiv_rn(tot, a.temperature);
-        sl[v0 + r] = l;
-        if (a.logits_out) a.logits_out[static_cast<long long>(b) * a.V + v0 + r] = l;
-      }
-    }
+  // ---- logits / temperature (minGPT.py:346); the accumulator is cleared for the next position's split-K head GEMM
+  float* lrow = a.logits_acc + static_cast<long long>(b) * a.V;
+  for (int i = t; i < a.V; i += SAMPLE_THREADS) {
+    const float l = __fdiv_rn(lrow[i], a.temperature);
+    lrow[i] = 0.f;
+    sl[i] = l;
+    if (a.logits_out) a.logits_out[static_cast<long long>(b) * a.V + i] = l;
   }
   __syncthreads();
 
@@ -620,43 +574,83 @@ sample_step_kernel(const SampleArgs a) {
   const float total = block_reduce(ls, red, false);
   __syncthreads();
 
-  // ---- multinomial(probs, 1) (:354) or topk(probs, 1) (:356)
-  if (t == 0) {
-    int tok = 0;
+  // ---- multinomial(probs, 1) (:354) or topk(probs, 1) (:356), by warp 0: every lane owns a contiguous slice
+  if (t < 32) {
+    const int per = (a.V + 31) / 32;
+    const int lo = lane * per, hi = min(lo + per, a.V);
+    int tok;
     if (a.do_sample) {
-      const float u = philox_uniform(a.seed, static_cast<uint32_t>(pos), static_cast<uint32_t>(b));
-      const float target = u * total;
-      float cum = 0.f;
-      int last_nonzero = 0;
-      tok = -1;
-      for (int i = 0; i < a.V; ++i) {
-        const float p = sl[i];
-        if (p > 0.f) last_nonzero = i;
-        cum += p;
-        if (tok < 0 && cum > target && p > 0.f) tok = i;
+      float mine = 0.f;
+      for (int i = lo; i < hi; ++i) mine += sl[i];
+      float incl = mine;                       // inclusive scan over lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
       }
-      if (tok < 0) tok = last_nonzero;
+      const float u = philox_uniform(a.seed, static_cast<uint32_t>(pos), static_cast<uint32_t>(b));
+      const float target = u * __shfl_sync(0xffffffffu, incl, 31);
+      const float excl = incl - mine;
+      // first index whose cumulative probability exceeds the target
+      int cand = 0x7fffffff;
+      if (mine > 0.f && incl > target && excl <= target) {
+        float cum = excl;
+        for (int i = lo; i < hi; ++i) {
+          cum += sl[i];
+          if (sl[i] > 0.f && cum > target) {
+            cand = i;
+            break;
+          }
+        }
+      }
+      // fallbacks for rounding at the upper end: the last index with non-zero probability
+      int last_nz = -1;
+      for (int i = lo; i < hi; ++i)
+        if (sl[i] > 0.f) last_nz = i;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        last_nz = max(last_nz, __shfl_xor_sync(0xffffffffu, last_nz, o));
+      }
+      tok = (cand != 0x7fffffff) ? cand : max(last_nz, 0);
     } else {
       float best = -1.f;
-      for (int i = 0; i < a.V; ++i)
+      int bi = 0x7fffffff;
+      for (int i = lo; i < hi; ++i)
         if (sl[i] > best) {
           best = sl[i];
-          tok = i;
+          bi = i;
         }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bi = oi;
+        }
+      }
+      tok = bi;
     }
-    s_tok = tok;
-    const int slot = pos + 1 - a.m;
-    if (slot >= 0 && slot < a.tokens_ld) a.tokens[static_cast<long long>(b) * a.tokens_ld + slot] = tok;
+    (void)total;
+    if (lane == 0) {
+      s_tok = tok;
+      const int slot = pos + 1 - a.m;
+      if (slot >= 0 && slot < a.tokens_ld) a.tokens[static_cast<long long>(b) * a.tokens_ld + slot] = tok;
+    }
   }
   __syncthreads();
   const int tok = s_tok;
 
   // ---- embedding of the sampled token for the next position (minGPT.py:170-180)
   if (a.x_next && pos + 1 < a.block_size) {
-    const float* te = a.tok_emb + static_cast<long long>(tok) * a.C;
-    const float* pe = a.pos_emb + static_cast<long long>(pos + 1) * a.C;
-    float* xn = a.x_next + static_cast<long long>(b) * a.C;
-    for (int i = t; i < a.C; i += SAMPLE_THREADS) xn[i] = __ldg(te + i) + __ldg(pe + i);
+    const float4* te = reinterpret_cast<const float4*>(a.tok_emb + static_cast<long long>(tok) * a.C);
+    const float4* pe = reinterpret_cast<const float4*>(a.pos_emb + static_cast<long long>(pos + 1) * a.C);
+    float4* xn = reinterpret_cast<float4*>(a.x_next + static_cast<long long>(b) * a.C);
+    for (int i = t; i < a.C / 4; i += SAMPLE_THREADS) {
+      const float4 p = __ldg(te + i), q = __ldg(pe + i);
+      xn[i] = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
+    }
   }
 
   // ---- the last CTA to finish advances the position (every CTA read *pos_ptr before arriving)
@@ -741,12 +735,12 @@ int gpt_gelu_bf16(float* h32, long long n, __nv_bfloat16* out, bool zero_consume
 }
 
 int gpt_sample_step(const SampleArgs& a, cudaStream_t s, bool pdl) {
-  MGV_REQUIRE(a.done_counter && a.pos_ptr, "sample: null state pointers");
+  MGV_REQUIRE(a.done_counter && a.pos_ptr && a.logits_acc, "sample: null state pointers");
   MGV_REQUIRE(a.V >= 1 && a.V <= SAMPLE_MAX_V, "sample: vocab=%d unsupported (<= %d)", a.V, SAMPLE_MAX_V);
-  MGV_REQUIRE(a.C % 8 == 0, "sample: C=%d", a.C);
+  MGV_REQUIRE(a.C % 4 == 0, "sample: C=%d", a.C);
   MGV_REQUIRE(a.temperature > 0.f, "sample: temperature must be > 0");
   if (a.B == 0) return MGV_OK;
-  const size_t smem = (static_cast<size_t>(a.C) + a.V) * 4;
+  const size_t smem = static_cast<size_t>(a.V) * 4;
   LaunchCfg lc(dim3(a.B), dim3(SAMPLE_THREADS), smem, s, pdl);
   MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, sample_step_kernel, a));
   return MGV_OK;

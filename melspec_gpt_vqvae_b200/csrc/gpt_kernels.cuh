@@ -37,17 +37,14 @@ int gpt_attention_decode(float* qkv32, int B, int nh, const int* pos_ptr, __nv_b
 int gpt_gelu_bf16(float* h32, long long n, __nv_bfloat16* out, bool zero_consumed, cudaStream_t s, bool pdl);
 
 struct SampleArgs {
-  const float* x;          // [B, C] final residual stream of the step
-  const float* lnf_w;
-  const float* lnf_b;
-  const __nv_bfloat16* whead;  // [V, C]
+  float* logits_acc;       // [B, V] fp32: head logits of this position (split-K accumulator; cleared here after use)
   int B, C, V;
   float temperature;
   int top_k;               // 0 = no top-k
   int do_sample;           // 0 = greedy (torch.topk(probs, 1)), 1 = multinomial
   unsigned long long seed;
   int* pos_ptr;            // device: position of the row just processed; incremented here
-  long long* tokens;       // [B, tokens_ld]; token for sequence slot (pos - m + 1) ... see kernel
+  long long* tokens;       // [B, tokens_ld]; the sampled token goes to slot pos + 1 - m
   int tokens_ld;
   int m;                   // prefix length (cond_size)
   const float* tok_emb;
