@@ -68,7 +68,12 @@ struct Gpt {
   int dec_B = 0;  // decode batch capacity
   float *dx = nullptr, *dqkv32 = nullptr, *dh32 = nullptr, *dlogits = nullptr;
   __nv_bfloat16 *dln = nullptr, *dy = nullptr, *dh = nullptr, *kv = nullptr;
-  int* d_state = nullptr;  // [0]=pos, [1]=done counter, [2]=err flag
+  int* d_state = nullptr;  // [0]=pos, [1]=done counter, [2]=err flag, [4..5]=Philox seed (u64)
+  long long* dtokens = nullptr;  // [dec_B, block_size] token buffer the sampler writes (stable address for the graph)
+  // cached decode-step graph (valid while the key matches and the workspaces are not reallocated)
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  struct { int B, m, top_k, do_sample; float temperature; long long per_step; } graph_key = {0, 0, 0, 0, 0.f, 0};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   bool pdl = false;
@@ -144,7 +149,10 @@ int ensure_prefill_ws(Gpt* g, int rows) {
 int ensure_decode_ws(Gpt* g, int B) {
   if (B <= g->dec_B) return MGV_OK;
   cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
-  cudaFree(g->kv); cudaFree(g->dlogits);
+  cudaFree(g->kv); cudaFree(g->dlogits); cudaFree(g->dtokens);
+  g->dtokens = nullptr;
+  if (g->graph_exec) { cudaGraphExecDestroy(g->graph_exec); g->graph_exec = nullptr; }
+  if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }
   g->dx = g->dqkv32 = g->dh32 = g->dlogits = nullptr;
   g->dln = g->dy = g->dh = g->kv = nullptr;
   g->dec_B = 0;
@@ -153,6 +161,7 @@ int ensure_decode_ws(Gpt* g, int B) {
   MGV_CHECK_CUDA(cudaMalloc(&g->dqkv32, R * 3 * C * 4));
   MGV_CHECK_CUDA(cudaMalloc(&g->dh32, R * 4 * C * 4));
   MGV_CHECK_CUDA(cudaMalloc(&g->dlogits, R * static_cast<size_t>(g->Vout) * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&g->dtokens, R * static_cast<size_t>(g->cfg.block_size + 1) * 8));
   MGV_CHECK_CUDA(cudaMalloc(&g->dln, R * C * 2));
   MGV_CHECK_CUDA(cudaMalloc(&g->dy, R * C * 2));
   MGV_CHECK_CUDA(cudaMalloc(&g->dh, R * 4 * C * 2));
@@ -257,8 +266,8 @@ int gpt_create(const GptConfig* cfg, Gpt** out) {
   carve_params(g, static_cast<char*>(g->slab), &total);
   g->n_tensors = 6 + 12 * g->L;
   g->loaded.assign(g->n_tensors, 0);
-  cudaMalloc(&g->d_state, 4 * sizeof(int));
-  cudaMemset(g->d_state, 0, 4 * sizeof(int));
+  cudaMalloc(&g->d_state, 8 * sizeof(int));
+  cudaMemset(g->d_state, 0, 8 * sizeof(int));
   cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&g->ev_in, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&g->ev_out, cudaEventDisableTiming);
@@ -285,7 +294,9 @@ int gpt_destroy(Gpt* g) {
   cudaFree(g->slab);
   cudaFree(g->x); cudaFree(g->ln); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->h);
   cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
-  cudaFree(g->kv); cudaFree(g->dlogits);
+  cudaFree(g->kv); cudaFree(g->dlogits); cudaFree(g->dtokens);
+  if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
   cudaFree(g->d_state);
   if (g->stream) cudaStreamDestroy(g->stream);
   if (g->ev_in) cudaEventDestroy(g->ev_in);
@@ -478,10 +489,14 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   MGV_CHECK_CUDA(cudaEventRecord(g->ev_in, caller));
   MGV_CHECK_CUDA(cudaStreamWaitEvent(s, g->ev_in, 0));
   MGV_TRY(ensure_decode_ws(g, B));
-  const int ld = t0 + steps;
-  if (t0 > 0)
+  const int ld = t0 + steps;                 // row length of the caller's x_out
+  const int tld = g->cfg.block_size + 1;     // row length of the internal token buffer
+  if (t0 > 0) {
     MGV_CHECK_CUDA(cudaMemcpy2DAsync(x_out, static_cast<size_t>(ld) * 8, x0, static_cast<size_t>(t0) * 8,
                                      static_cast<size_t>(t0) * 8, B, cudaMemcpyDeviceToDevice, s));
+    MGV_CHECK_CUDA(cudaMemcpy2DAsync(g->dtokens, static_cast<size_t>(tld) * 8, x0, static_cast<size_t>(t0) * 8,
+                                     static_cast<size_t>(t0) * 8, B, cudaMemcpyDeviceToDevice, s));
+  }
   if (steps == 0) {
     MGV_CHECK_CUDA(cudaEventRecord(g->ev_out, s));
     MGV_CHECK_CUDA(cudaStreamWaitEvent(caller, g->ev_out, 0));
@@ -510,49 +525,78 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   MGV_CHECK_CUDA(cudaMemsetAsync(g->dlogits, 0, static_cast<size_t>(B) * g->Vout * 4, s));
   const int init_state[2] = {T0 - 1, 0};
   MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state, init_state, 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+  MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state + 4, &seed, sizeof(seed), cudaMemcpyHostToDevice, s));
 
   SampleArgs sa;
   memset(&sa, 0, sizeof(sa));
   sa.logits_acc = g->dlogits;
   sa.B = B; sa.C = g->C; sa.V = g->V;
-  sa.temperature = temperature; sa.top_k = top_k; sa.do_sample = do_sample; sa.seed = seed;
+  sa.temperature = temperature; sa.top_k = top_k; sa.do_sample = do_sample;
+  sa.seed_ptr = reinterpret_cast<const unsigned long long*>(g->d_state + 4);
   sa.pos_ptr = g->d_state;
-  sa.tokens = x_out; sa.tokens_ld = ld; sa.m = m;
+  sa.tokens = g->dtokens; sa.tokens_ld = tld; sa.m = m;
   sa.tok_emb = g->tok_emb; sa.pos_emb = g->pos_emb; sa.block_size = g->cfg.block_size;
   sa.x_next = g->dx; sa.logits_out = nullptr;
   sa.done_counter = reinterpret_cast<unsigned int*>(g->d_state + 1);
 
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t tmp_graph = nullptr;
+  cudaGraphExec_t tmp_exec = nullptr;
   if (use_graph) {
-    MGV_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const long long before = g->launches;
-    int rc = enqueue_decode_step(g, B, sa, att_out, Tf, s);
-    const long long per_step = g->launches - before;
-    cudaError_t ce = cudaStreamEndCapture(s, &graph);
-    if (rc != MGV_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return rc;
+    // the decode-step graph only depends on (B, m, sampler settings) and on handle-owned buffers, so it is
+    // captured once and replayed for every position of every later call with the same settings; a request for
+    // the attention map (caller-owned buffer) gets a one-off graph
+    const bool cacheable = att_out == nullptr;
+    const bool hit = cacheable && g->graph_exec && g->graph_key.B == B && g->graph_key.m == m &&
+                     g->graph_key.top_k == top_k && g->graph_key.do_sample == do_sample &&
+                     g->graph_key.temperature == temperature;
+    cudaGraphExec_t exec = hit ? g->graph_exec : nullptr;
+    long long per_step = hit ? g->graph_key.per_step : 0;
+    if (!hit) {
+      cudaGraph_t graph = nullptr;
+      MGV_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const long long before = g->launches;
+      const int rc = enqueue_decode_step(g, B, sa, att_out, Tf, s);
+      per_step = g->launches - before;
+      g->launches = before;
+      const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc != MGV_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      MGV_CHECK_CUDA(ce);
+      MGV_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      if (cacheable) {
+        if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
+        if (g->graph) cudaGraphDestroy(g->graph);
+        g->graph = graph;
+        g->graph_exec = exec;
+        g->graph_key = {B, m, top_k, do_sample, temperature, per_step};
+      } else {
+        tmp_graph = graph;
+        tmp_exec = exec;
+      }
     }
-    MGV_CHECK_CUDA(ce);
-    MGV_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     for (int k = 0; k < steps; ++k) {
-      cudaError_t le = cudaGraphLaunch(exec, s);
+      const cudaError_t le = cudaGraphLaunch(exec, s);
       if (le != cudaSuccess) {
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(graph);
+        if (tmp_exec) cudaGraphExecDestroy(tmp_exec);
+        if (tmp_graph) cudaGraphDestroy(tmp_graph);
         MGV_CHECK_CUDA(le);
       }
     }
-    g->launches = before + per_step * steps;
+    g->launches += per_step * steps;
   } else {
     for (int k = 0; k < steps; ++k) MGV_TRY(enqueue_decode_step(g, B, sa, att_out, Tf, s));
   }
-  cudaError_t e1 = cudaEventRecord(g->ev_out, s);
-  cudaError_t e2 = cudaStreamWaitEvent(caller, g->ev_out, 0);
+  // generated tokens: internal buffer columns [t0, t0+steps) -> x_out
+  const cudaError_t e0 = cudaMemcpy2DAsync(x_out + t0, static_cast<size_t>(ld) * 8, g->dtokens + t0, static_cast<size_t>(tld) * 8,
+                                           static_cast<size_t>(steps) * 8, B, cudaMemcpyDeviceToDevice, s);
+  const cudaError_t e1 = cudaEventRecord(g->ev_out, s);
+  const cudaError_t e2 = cudaStreamWaitEvent(caller, g->ev_out, 0);
   const int rc = read_err_flag(g, s, "gpt_generate");  // synchronises s
-  if (exec) cudaGraphExecDestroy(exec);
-  if (graph) cudaGraphDestroy(graph);
+  if (tmp_exec) cudaGraphExecDestroy(tmp_exec);
+  if (tmp_graph) cudaGraphDestroy(tmp_graph);
+  MGV_CHECK_CUDA(e0);
   MGV_CHECK_CUDA(e1);
   MGV_CHECK_CUDA(e2);
   return rc;

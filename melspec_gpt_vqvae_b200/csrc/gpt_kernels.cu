@@ -300,14 +300,16 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T, int nh,
 // ------------------------------------------------------------------ decode attention
 // One CTA per (sequence, head), 128 threads = 16 key groups x 8 dim chunks: thread (kg, dc) owns the 8
 // head dims [8*dc, 8*dc+8) (one 16-byte load per key) of keys kg, kg+16, ... ; keys are walked in passes of
-// 128 (8 independent loads per thread in flight).  A warp's load covers 4 consecutive 128-byte cache rows
-// (512 contiguous bytes).  <= 64 registers and ~2 KB smem so that all B*n_head CTAs are resident in ONE wave
-// (7 per SM at B=64): the step's latency is then one dependency chain, not one per wave.  The V loads of the
-// first pass are issued before the softmax reductions.
+// 64 (4 loads per thread) with two register buffers, so the loads of pass p+1 are in flight while pass p is
+// reduced: the cache streams continuously instead of in load / compute phases.  A warp's load covers 4
+// consecutive 128-byte cache rows (512 contiguous bytes).  <= 72 registers and ~2 KB smem so that all
+// B*n_head CTAs are resident in ONE wave (7 per SM at B=64): the step's latency is one dependency chain,
+// not one per wave.  The first K pass is issued before the grid dependency resolves, the first V pass before
+// the softmax reductions.
 constexpr int AD_THREADS = 128;
 constexpr int AD_KG = 16;                 // key groups
-constexpr int AD_KPP = 8;                 // keys per thread per pass
-constexpr int AD_PASS = AD_KG * AD_KPP;   // 128 keys per pass
+constexpr int AD_KPP = 4;                 // keys per thread per pass
+constexpr int AD_PASS = AD_KG * AD_KPP;   // 64 keys per pass
 
 __global__ void __launch_bounds__(AD_THREADS, 7)
 attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ pos_ptr,
@@ -330,14 +332,19 @@ attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ po
   const __nv_bfloat16* vc = vcache + (static_cast<long long>(b) * nh + h) * Tmax * GPT_HEAD_DIM + dc * 8;
   const int npass = pos / AD_PASS + 1;
 
-  // ---- first pass of K rows: positions < pos were written by earlier steps, so load before the dependency
-  uint4 kreg[AD_KPP];
+  auto load_rows = [&](const __nv_bfloat16* base, const __nv_bfloat16* fresh, int p, uint4 (&buf)[AD_KPP]) {
 #pragma unroll
-  for (int i = 0; i < AD_KPP; ++i) {
-    const int j = kg + AD_KG * i;
-    kreg[i] = make_uint4(0, 0, 0, 0);
-    if (j < pos) kreg[i] = *reinterpret_cast<const uint4*>(kc + static_cast<long long>(j) * GPT_HEAD_DIM);
-  }
+    for (int i = 0; i < AD_KPP; ++i) {
+      const int j = p * AD_PASS + kg + AD_KG * i;
+      buf[i] = make_uint4(0, 0, 0, 0);
+      if (j < pos) buf[i] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(j) * GPT_HEAD_DIM);
+      else if (j == pos && fresh) buf[i] = *reinterpret_cast<const uint4*>(fresh + dc * 8);
+    }
+  };
+
+  // ---- first pass of K rows: positions < pos were written by earlier steps, so load before the dependency
+  uint4 b0[AD_KPP], b1[AD_KPP];
+  load_rows(kc, nullptr, 0, b0);
   pdl_wait();
   if (t < GPT_HEAD_DIM) {
     float* base = qkv32 + static_cast<long long>(b) * 3 * C + h * GPT_HEAD_DIM + t;
@@ -364,19 +371,11 @@ attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ po
 #pragma unroll
   for (int e = 0; e < 8; ++e) q8[e] = sq[dc * 8 + e];
   float lmax = -INFINITY;
-  for (int p = 0; p < npass; ++p) {
-    if (p > 0) {
-#pragma unroll
-      for (int i = 0; i < AD_KPP; ++i) {
-        const int j = p * AD_PASS + kg + AD_KG * i;
-        kreg[i] = make_uint4(0, 0, 0, 0);
-        if (j < pos) kreg[i] = *reinterpret_cast<const uint4*>(kc + static_cast<long long>(j) * GPT_HEAD_DIM);
-      }
-    }
+  auto score_pass = [&](int p, const uint4 (&buf)[AD_KPP]) {
 #pragma unroll
     for (int i = 0; i < AD_KPP; ++i) {
       const int j = p * AD_PASS + kg + AD_KG * i;
-      uint4 kv = kreg[i];
+      uint4 kv = buf[i];
       if (j == pos) kv = *reinterpret_cast<const uint4*>(sk + dc * 8);
       const float2 a = unpack_bf16x2(kv.x), bq = unpack_bf16x2(kv.y), c = unpack_bf16x2(kv.z), d = unpack_bf16x2(kv.w);
       float s = q8[0] * a.x;
@@ -396,16 +395,15 @@ attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ po
         lmax = fmaxf(lmax, s);
       }
     }
+  };
+  for (int p = 0; p < npass; p += 2) {
+    if (p + 1 < npass) load_rows(kc, nullptr, p + 1, b1);
+    score_pass(p, b0);
+    if (p + 2 < npass) load_rows(kc, nullptr, p + 2, b0);
+    if (p + 1 < npass) score_pass(p + 1, b1);
   }
   // ---- V rows of the first pass: issue now, consume after the softmax reductions
-  uint4 vreg[AD_KPP];
-#pragma unroll
-  for (int i = 0; i < AD_KPP; ++i) {
-    const int j = kg + AD_KG * i;
-    vreg[i] = make_uint4(0, 0, 0, 0);
-    if (j < pos) vreg[i] = *reinterpret_cast<const uint4*>(vc + static_cast<long long>(j) * GPT_HEAD_DIM);
-    else if (j == pos) vreg[i] = *reinterpret_cast<const uint4*>(sv + dc * 8);
-  }
+  load_rows(vc, sv, 0, b0);
   lmax = warp_max(lmax);
   if (lane == 0) red[warp] = lmax;
   __syncthreads();
@@ -426,23 +424,14 @@ attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ po
   }
   // ---- PV
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int p = 0; p < npass; ++p) {
-    if (p > 0) {
-#pragma unroll
-      for (int i = 0; i < AD_KPP; ++i) {
-        const int j = p * AD_PASS + kg + AD_KG * i;
-        vreg[i] = make_uint4(0, 0, 0, 0);
-        if (j < pos) vreg[i] = *reinterpret_cast<const uint4*>(vc + static_cast<long long>(j) * GPT_HEAD_DIM);
-        else if (j == pos) vreg[i] = *reinterpret_cast<const uint4*>(sv + dc * 8);
-      }
-    }
+  auto pv_pass = [&](int p, const uint4 (&buf)[AD_KPP]) {
 #pragma unroll
     for (int i = 0; i < AD_KPP; ++i) {
       const int j = p * AD_PASS + kg + AD_KG * i;
       if (j <= pos) {
         const float pj = ss[j];
-        const float2 a = unpack_bf16x2(vreg[i].x), bq = unpack_bf16x2(vreg[i].y), c = unpack_bf16x2(vreg[i].z),
-                     d = unpack_bf16x2(vreg[i].w);
+        const float2 a = unpack_bf16x2(buf[i].x), bq = unpack_bf16x2(buf[i].y), c = unpack_bf16x2(buf[i].z),
+                     d = unpack_bf16x2(buf[i].w);
         acc[0] = fmaf(pj, a.x, acc[0]);
         acc[1] = fmaf(pj, a.y, acc[1]);
         acc[2] = fmaf(pj, bq.x, acc[2]);
@@ -453,6 +442,12 @@ attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ po
         acc[7] = fmaf(pj, d.y, acc[7]);
       }
     }
+  };
+  for (int p = 0; p < npass; p += 2) {
+    if (p + 1 < npass) load_rows(vc, sv, p + 1, b1);
+    pv_pass(p, b0);
+    if (p + 2 < npass) load_rows(vc, sv, p + 2, b0);
+    if (p + 1 < npass) pv_pass(p + 1, b1);
   }
   // reduce the 4 key groups of a warp (lanes with equal dc), then the 4 warps through smem
 #pragma unroll
@@ -588,7 +583,7 @@ sample_step_kernel(const SampleArgs a) {
         const float up = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += up;
       }
-      const float u = philox_uniform(a.seed, static_cast<uint32_t>(pos), static_cast<uint32_t>(b));
+      const float u = philox_uniform(*a.seed_ptr, static_cast<uint32_t>(pos), static_cast<uint32_t>(b));
       const float target = u * __shfl_sync(0xffffffffu, incl, 31);
       const float excl = incl - mine;
       // first index whose cumulative probability exceeds the target
@@ -735,7 +730,7 @@ int gpt_gelu_bf16(float* h32, long long n, __nv_bfloat16* out, bool zero_consume
 }
 
 int gpt_sample_step(const SampleArgs& a, cudaStream_t s, bool pdl) {
-  MGV_REQUIRE(a.done_counter && a.pos_ptr && a.logits_acc, "sample: null state pointers");
+  MGV_REQUIRE(a.done_counter && a.pos_ptr && a.logits_acc && a.seed_ptr, "sample: null state pointers");
   MGV_REQUIRE(a.V >= 1 && a.V <= SAMPLE_MAX_V, "sample: vocab=%d unsupported (<= %d)", a.V, SAMPLE_MAX_V);
   MGV_REQUIRE(a.C % 4 == 0, "sample: C=%d", a.C);
   MGV_REQUIRE(a.temperature > 0.f, "sample: temperature must be > 0");

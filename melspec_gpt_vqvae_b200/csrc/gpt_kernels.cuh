@@ -42,7 +42,7 @@ struct SampleArgs {
   float temperature;
   int top_k;               // 0 = no top-k
   int do_sample;           // 0 = greedy (torch.topk(probs, 1)), 1 = multinomial
-  unsigned long long seed;
+  const unsigned long long* seed_ptr;   // device: Philox key (read per step, so a captured graph can be reused)
   int* pos_ptr;            // device: position of the row just processed; incremented here
   long long* tokens;       // [B, tokens_ld]; the sampled token goes to slot pos + 1 - m
   int tokens_ld;
