@@ -11,6 +11,7 @@
 // producer issues the B (weight) loads of the first ring pass BEFORE griddepcontrol.wait,
 // so weights stream from HBM while the upstream kernel is still finishing; only the A
 // (activation) loads wait for the dependency.
+#include <stdlib.h>
 #include "gemm_tc.cuh"
 
 namespace mgv {
@@ -41,6 +42,148 @@ struct KParams {
   int evict_first_w;   // L2 evict-first hint on the weight operand
   int transpose_out;   // swap-AB: weights are the A operand, output written transposed
 };
+
+// Row-major epilogue of one accumulator tile: this thread owns accumulator row (TMEM lane) `quarter*32+lane`
+// and walks the BN columns in chunks of 32 (bias / GELU / residual / bf16 or fp32 store / split-K reduction /
+// GroupNorm partial sums into this warp's shared-memory bins).
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const KParams& p, uint32_t tmem_base, int quarter, int lane, bool row_ok,
+                                              long long out_row, int n0, bool add_bias, float* s_bins,
+                                              int c_begin = 0, int c_end = BN / 32) {
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (add_bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          v[4 * j + 0] += b.x;
+          v[4 * j + 1] += b.y;
+          v[4 * j + 2] += b.z;
+          v[4 * j + 3] += b.w;
+        }
+      }
+      if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU || p.epi == EPI_BF16_RESID) {
+        if (p.epi == EPI_BF16_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (p.epi == EPI_BF16_RESID && row_ok) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + out_row + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = __ldg(r4 + j);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(w[e]);
+              v[8 * j + 2 * e] += f.x;
+              v[8 * j + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        if (row_ok) {
+          uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_row + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (p.gn_sum != nullptr) {
+          // GroupNorm statistics of the stored (bf16-rounded) values; a tile never spans images.
+          // Per lane: (sum, sumsq) of each channel group of this 32-column chunk -> 2*(32/gch) <= 16 values;
+          // a transposing butterfly (16 shuffles) leaves one fully reduced value per lane pair, which goes to
+          // the per-CTA shared-memory bins (flushed once per CTA after the chunk loop).
+          const int gch = p.gn_group_ch;          // 4, 8 or 16 channels per group
+          float st[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) st[i] = 0.f;
+          if (row_ok) {
+            float sq[16], sm[16];                 // per channel pair
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 f = unpack_bf16x2(pk[j]);
+              sm[j] = f.x + f.y;
+              sq[j] = f.x * f.x + f.y * f.y;
+            }
+            if (gch == 4) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                st[2 * g] = sm[2 * g] + sm[2 * g + 1];
+                st[2 * g + 1] = sq[2 * g] + sq[2 * g + 1];
+              }
+            } else if (gch == 8) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                st[2 * g] = (sm[4 * g] + sm[4 * g + 1]) + (sm[4 * g + 2] + sm[4 * g + 3]);
+                st[2 * g + 1] = (sq[4 * g] + sq[4 * g + 1]) + (sq[4 * g + 2] + sq[4 * g + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  a += sm[8 * g + e];
+                  b += sq[8 * g + e];
+                }
+                st[2 * g] = a;
+                st[2 * g + 1] = b;
+              }
+            }
+          }
+          // butterfly: after the steps with offsets 16, 8, 4, 2 lane l holds value index (l >> 1) & 15
+#pragma unroll
+          for (int step = 0; step < 4; ++step) {
+            const int off = 16 >> step, n = 8 >> step;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              const float send = upper ? st[i] : st[i + n];
+              const float keep = upper ? st[i + n] : st[i];
+              st[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
+          const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          const int nvals = 2 * (32 / gch);
+          // each warp owns its bins (one writer per bin): plain, deterministic accumulation
+          if ((lane & 1) == 0 && vidx < nvals) s_bins[quarter * 64 + c * nvals + vidx] += st[0];
+        }
+      } else if (row_ok) {
+        float* o = static_cast<float*>(p.out) + out_row + col0;
+        if (p.epi == EPI_F32_ATOMIC) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        } else {
+          if (p.epi == EPI_F32_RESID) {
+            const float4* r4 = reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + out_row + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q = r4[j];
+              v[4 * j + 0] += q.x;
+              v[4 * j + 1] += q.y;
+              v[4 * j + 2] += q.z;
+              v[4 * j + 3] += q.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+}
 
 // DECODE = true: the swap-AB weight-streaming form only (plain A operand, transposed epilogue) -- the decode
 // loop launches this kernel ~100 times per position for a few microseconds each, so its code is kept minimal.
@@ -240,139 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     } else if constexpr (!DECODE) {
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int col0 = n0 + c * 32;
-      if (col0 >= p.N) break;  // warp-uniform
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (add_bias) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(b4 + j);
-          v[4 * j + 0] += b.x;
-          v[4 * j + 1] += b.y;
-          v[4 * j + 2] += b.z;
-          v[4 * j + 3] += b.w;
-        }
-      }
-      if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU || p.epi == EPI_BF16_RESID) {
-        if (p.epi == EPI_BF16_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (p.epi == EPI_BF16_RESID && row_ok) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + out_row + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 q = __ldg(r4 + j);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(w[e]);
-              v[8 * j + 2 * e] += f.x;
-              v[8 * j + 2 * e + 1] += f.y;
-            }
-          }
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-        if (row_ok) {
-          uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_row + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        }
-        if (p.gn_sum != nullptr) {
-          // GroupNorm statistics of the stored (bf16-rounded) values; a tile never spans images.
-          // Per lane: (sum, sumsq) of each channel group of this 32-column chunk -> 2*(32/gch) <= 16 values;
-          // a transposing butterfly (16 shuffles) leaves one fully reduced value per lane pair, which goes to
-          // the per-CTA shared-memory bins (flushed once per CTA after the chunk loop).
-          const int gch = p.gn_group_ch;          // 4, 8 or 16 channels per group
-          float st[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) st[i] = 0.f;
-          if (row_ok) {
-            float sq[16], sm[16];                 // per channel pair
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 f = unpack_bf16x2(pk[j]);
-              sm[j] = f.x + f.y;
-              sq[j] = f.x * f.x + f.y * f.y;
-            }
-            if (gch == 4) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                st[2 * g] = sm[2 * g] + sm[2 * g + 1];
-                st[2 * g + 1] = sq[2 * g] + sq[2 * g + 1];
-              }
-            } else if (gch == 8) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                st[2 * g] = (sm[4 * g] + sm[4 * g + 1]) + (sm[4 * g + 2] + sm[4 * g + 3]);
-                st[2 * g + 1] = (sq[4 * g] + sq[4 * g + 1]) + (sq[4 * g + 2] + sq[4 * g + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                float a = 0.f, b = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  a += sm[8 * g + e];
-                  b += sq[8 * g + e];
-                }
-                st[2 * g] = a;
-                st[2 * g + 1] = b;
-              }
-            }
-          }
-          // butterfly: after the steps with offsets 16, 8, 4, 2 lane l holds value index (l >> 1) & 15
-#pragma unroll
-          for (int step = 0; step < 4; ++step) {
-            const int off = 16 >> step, n = 8 >> step;
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              const float send = upper ? st[i] : st[i + n];
-              const float keep = upper ? st[i + n] : st[i];
-              st[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-          }
-          st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
-          const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          const int nvals = 2 * (32 / gch);
-          // each warp owns its bins (one writer per bin): plain, deterministic accumulation
-          if ((lane & 1) == 0 && vidx < nvals) s_bins[quarter * 64 + c * nvals + vidx] += st[0];
-        }
-      } else if (row_ok) {
-        float* o = static_cast<float*>(p.out) + out_row + col0;
-        if (p.epi == EPI_F32_ATOMIC) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            atomicAdd(reinterpret_cast<float4*>(o) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-        } else {
-          if (p.epi == EPI_F32_RESID) {
-            const float4* r4 = reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + out_row + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 q = r4[j];
-              v[4 * j + 0] += q.x;
-              v[4 * j + 1] += q.y;
-              v[4 * j + 2] += q.z;
-              v[4 * j + 3] += q.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      }
-    }
+      epilogue_rows<BN>(p, tmem_base, quarter, lane, row_ok, out_row, n0, add_bias, s_bins);
     }  // !DECODE
     if (!DECODE && p.gn_sum != nullptr) {
       // one plain store per CTA and bin into this tile's slot (deterministic; folded by vqvae_gn_finalize)
@@ -392,6 +403,190 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
+  }
+}
+
+
+// ---------------------------------------------------------------- persistent variant (large grids)
+// One CTA per SM loops over output tiles.  The smem ring keeps streaming across tile boundaries and the
+// accumulator is double buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the MMAs of
+// tile i+1 -- the canonical warp-specialised Blackwell GEMM.  Used for the implicit-GEMM convolutions and the
+// prefill GEMMs; the decode GEMMs (one tile per CTA) use gemm_tc_kernel<BN, true>.
+struct PTile {
+  int m0, n0, img, x0, y0;
+  long long stats_slot;   // index of this tile's GroupNorm partial-sum slot
+};
+
+__device__ __forceinline__ PTile decode_tile(const KParams& p, int tile, int n_tiles, int BN) {
+  PTile t;
+  const int mt = tile / n_tiles;
+  t.n0 = (tile - mt * n_tiles) * BN;
+  t.m0 = 0; t.img = 0; t.x0 = 0; t.y0 = 0;
+  t.stats_slot = mt;
+  if (p.a_mode == A_PLAIN) {
+    t.m0 = mt * BM;
+  } else {
+    int r = mt;
+    const int tx = r % p.tiles_x;
+    r /= p.tiles_x;
+    const int ty = r % p.tiles_y;
+    t.img = r / p.tiles_y;
+    t.x0 = tx * p.wb;
+    t.y0 = ty * p.hb;
+  }
+  return t;
+}
+
+constexpr int PERSIST_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+
+template <int BN>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const KParams p, int m_tiles, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_bins = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][64]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = m_tiles * n_tiles;
+  const int nkb = p.K / BK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], PERSIST_THREADS - 64);   // every epilogue thread arrives
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      const int cblocks = (p.a_mode == A_PLAIN) ? 1 : (p.Cin / BK);
+      int it = 0;   // global k-block counter (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const PTile t = decode_tile(p, tile, n_tiles, BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* dst = smem + s * STAGE_BYTES;
+          if (p.a_mode == A_PLAIN) {
+            tma_load_2d(dst, &tmA, &full_bar[s], kb * BK, t.m0, kEvictNormal);
+          } else {
+            const int tap = kb / cblocks;
+            const int c0 = (kb - tap * cblocks) * BK;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            tma_load_4d(dst, &tmA, &full_bar[s], c0, t.x0 * p.stride + dx - p.pad, t.y0 * p.stride + dy - p.pad, t.img,
+                        kEvictNormal);
+          }
+          tma_load_2d(dst + A_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, t.n0, kEvictLast);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int as = lt & 1;
+        mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_acc, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(&tmem_full_bar[as]);
+      }
+    }
+  } else {
+    // =========================== epilogue ===========================
+    // warps 2..9: TMEM lane quarter = warp & 3 (hardware rule); the two warps of a quarter split the columns
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int NCH = BN / 32;
+    const int c_begin = (NCH >= 2) ? half * (NCH / 2) : 0;
+    const int c_end = (NCH >= 2) ? c_begin + NCH / 2 : (half == 0 ? 1 : 0);
+    const int r_local = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;      // epilogue thread index 0..255
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const PTile t = decode_tile(p, tile, n_tiles, BN);
+      const int as = lt & 1;
+      bool row_ok;
+      long long out_row;
+      if (p.a_mode == A_PLAIN) {
+        const int row = t.m0 + r_local;
+        row_ok = row < p.M;
+        out_row = static_cast<long long>(row) * p.ldo;
+      } else {
+        const int ly = r_local / p.wb, lx = r_local - ly * p.wb;
+        const int x = t.x0 + lx, y = t.y0 + ly;
+        row_ok = (x < p.W) && (y < p.H);
+        out_row = ((static_cast<long long>(t.img) * p.H + y) * p.W + x) * p.ldo;
+      }
+      if (p.gn_sum != nullptr) s_bins[et] = 0.f;   // 256 bins = [4 quarters][64]; cleared after the previous flush barrier
+      if (p.gn_sum != nullptr) asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
+      tc_fence_after();
+      epilogue_rows<BN>(p, tmem_base + as * BN, quarter, lane, row_ok, out_row, t.n0, p.bias != nullptr, s_bins, c_begin,
+                        c_end);
+      // accumulator fully read into registers: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[as]);
+      if (p.gn_sum != nullptr) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int nbins = (BN / p.gn_group_ch) * 2;
+        const int groups_total = p.N / p.gn_group_ch;
+        const int g0 = t.n0 / p.gn_group_ch;
+        if (et < nbins && g0 + (et >> 1) < groups_total)
+          p.gn_sum[(t.stats_slot * groups_total + g0 + (et >> 1)) * 2 + (et & 1)] =
+              (s_bins[et] + s_bins[64 + et]) + (s_bins[128 + et] + s_bins[192 + et]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // bins may be cleared for the next tile
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -522,12 +717,62 @@ int launch_tc(const GemmArgs& a, KParams& p) {
   return MGV_OK;
 }
 
+
+template <int BN>
+int launch_persist(const GemmArgs& a, KParams& p) {
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  p.kb_per_split = a.K / BK;
+  int stages = (196 * 1024) / STAGE_BYTES;   // one CTA per SM: use the whole shared memory as the ring
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * STAGE_BYTES + (2 * stages + 4) * 8 + 16 + 1024 + 1024;
+  CUtensorMap tmA, tmB;
+  int m_tiles;
+  if (a.a_mode == A_PLAIN) {
+    const int64_t lda = a.lda ? a.lda : a.K;
+    MGV_TRY(make_tmap_2d_bf16(&tmA, a.A, a.K, a.M, lda * 2, BK, BM));
+    m_tiles = ceil_div(a.M, BM);
+  } else {
+    MGV_TRY(make_tmap_nhwc_bf16(&tmA, a.A, a.Cin, a.Win, a.Hin, a.n_img, BK, p.wb, p.hb, a.stride));
+    m_tiles = p.tiles_x * p.tiles_y * a.n_img;
+  }
+  MGV_TRY(make_tmap_2d_bf16(&tmB, a.B, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, BN));
+  const int n_tiles = ceil_div(a.N, BN);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+    attr_set = true;
+  }
+  const int total = m_tiles * n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  LaunchCfg lc(dim3(grid), dim3(PERSIST_THREADS), smem, a.stream, false);
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_tc_persist_kernel<BN>, tmA, tmB, p, m_tiles, n_tiles));
+  return MGV_OK;
+}
+
 }  // namespace
 
 int gemm_bf16_tc(const GemmArgs& a) {
   KParams p;
   MGV_TRY(fill_params(a, p));
   if (a.a_mode == A_CONV3x3) MGV_REQUIRE(a.split_k == 1, "conv: split_k unsupported");
+  // large plain / conv problems: persistent kernel with double-buffered TMEM accumulators
+  static const bool no_persist = getenv("MGV_NO_PERSIST") != nullptr;
+  if (!a.transpose_out && a.split_k == 1 && !no_persist) {
+    const long long tiles = a.a_mode == A_PLAIN ? static_cast<long long>(ceil_div(a.M, BM)) * ceil_div(a.N, a.bn)
+                                                : static_cast<long long>(p.tiles_x) * p.tiles_y * a.n_img * ceil_div(a.N, a.bn);
+    if (tiles > 2LL * num_sms()) {
+      switch (a.bn) {
+        case 32: return launch_persist<32>(a, p);
+        case 64: return launch_persist<64>(a, p);
+        case 128: return launch_persist<128>(a, p);
+        case 256: return launch_persist<256>(a, p);
+        default: break;
+      }
+    }
+  }
   if (a.transpose_out) {   // decode form: compact kernel
     switch (a.bn) {
       case 32: return launch_tc<32, true>(a, p);

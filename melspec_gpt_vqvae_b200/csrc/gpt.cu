@@ -28,6 +28,7 @@ int cvt_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s) {
 }
 
 int pick_bn(int N) {
+  if (N % 256 == 0 && !getenv("MGV_NO_BN256")) return 256;   // 128x256 tiles: fewer L2 bytes per FLOP
   if (N % 128 == 0) return 128;
   if (N % 64 == 0) return 64;
   return 32;

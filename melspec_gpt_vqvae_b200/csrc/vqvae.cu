@@ -279,7 +279,7 @@ int conv3(Ctx& c, const Conv& w, const __nv_bfloat16* x, int Hin, int Win, int s
   a.M = c.B * a.H * a.W; a.N = w.cout; a.K = 9 * w.cin;
   a.epi = resid ? EPI_BF16_RESID : EPI_BF16;
   a.bias = w.b; a.out = out; a.resid = resid;
-  a.bn = 128;
+  a.bn = (w.cout % 256 == 0 && !getenv("MGV_NO_BN256")) ? 256 : 128;   // 128x256 tiles move 25% fewer L2 bytes per FLOP
   a.max_stages = conv_stages();   // 3 stages = 96 KB: two CTAs per SM, one's epilogue overlaps the other's MMAs
   static const bool unfused = getenv("MGV_UNFUSED_GNSTATS") != nullptr;   // debugging aid
   if (stats_out && !unfused) { a.gn_sum = c.v->gn_part; a.gn_group_ch = w.cout / 32; }
@@ -305,7 +305,7 @@ int conv1(Ctx& c, const __nv_bfloat16* wmat, const float* bias, int cin, int cou
   GemmArgs a;
   a.A = x; a.B = wmat; a.M = static_cast<int>(rows); a.N = cout; a.K = cin;
   a.epi = epi; a.bias = bias; a.out = out; a.resid = resid;
-  a.bn = 128;
+  a.bn = (cout % 256 == 0 && !getenv("MGV_NO_BN256")) ? 256 : 128;
   a.max_stages = conv_stages();
   a.stream = c.s;
   c.v->launches++;
