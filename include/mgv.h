@@ -161,6 +161,12 @@ int mgv_test_gemm(int impl, const void* A, const void* B, int M, int N, int K, i
 int mgv_test_gemm_swapab(int impl, const void* W, const void* X, int M, int N, int K, int epi, const float* bias,
                          void* out, const void* resid, int bn, int split_k, mgv_stream_t stream);
 
+/* Fused decode GEMMs: out[b, n] += sum_k act(src)[b, k] * W[n, k] + bias[n]; mode 0: act = gelu_erf,
+ * mode 1: act = LayerNorm(gamma, beta, eps 1e-5) with the row statistics exchanged between the split-K CTAs of a
+ * thread-block cluster.  W bf16 (Nw, K); src fp32 (B, K), B <= 64; out fp32 (B, Nw) accumulated in place. */
+int mgv_test_gemm_fused(int mode, const void* W, const float* src, int Nw, int B, int K, const float* gamma,
+                        const float* beta, const float* bias, float* out, int split_k, mgv_stream_t stream);
+
 /* 3x3 convolution (stride 1 pad 1, or stride 2 with the reference's (0,1,0,1) padding) over
  * NHWC bf16 input through the implicit-GEMM path (impl 0) or the SIMT reference (impl 1).
  * w: bf16 (Cout, 3, 3, Cin). */

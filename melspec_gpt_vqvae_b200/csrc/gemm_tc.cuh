@@ -63,6 +63,14 @@ struct GemmArgs {
 
 int gemm_bf16_tc(const GemmArgs& a);
 
+// Decode-step GEMMs with the activation operand produced in-kernel (gemm_decode_fused.cu):
+//   out[b, n] += sum_k act(src)[b, k] * W[n, k] (+ bias[n])   with act = gelu_erf or LayerNorm(gamma, beta, eps 1e-5).
+// W bf16 [Nw, K]; src fp32 [B, K]; out fp32 [B, ldo] accumulated with atomics (must hold the residual / zeros); B <= 64.
+int gemm_decode_gelu(const void* W, int Nw, int K, const float* src_f32, int B, const float* bias, float* out, long long ldo,
+                     int split_k, bool pdl, cudaStream_t stream);
+int gemm_decode_ln(const void* W, int Nw, int K, const float* x_f32, int B, const float* gamma, const float* beta,
+                   const float* bias, float* out, long long ldo, int split_k, bool pdl, cudaStream_t stream);
+
 // SIMT fp32 reference of the same contract (tests / on-device cross-checks only).
 int gemm_bf16_ref(const GemmArgs& a);
 

@@ -436,18 +436,41 @@ int decode_gemm(Gpt* g, const __nv_bfloat16* X, const __nv_bfloat16* W, const fl
 int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int att_T, cudaStream_t s) {
   const int C = g->C;
   const DecodeTiles& tl = g->tiles;
+  // Experimental fused path (MGV_FUSED_DECODE=1): LayerNorm applied inside the QKV / FC1 / head GEMMs (cluster-wide
+  // row statistics over distributed shared memory) and GELU inside FC2 -> 5 dependent kernels per layer instead of
+  // 8.  Measured SLOWER on B200 (1293 vs 1021 us per position): each fused kernel costs what its two parts cost
+  // (the GELU is recomputed by all 8 feature-tile CTAs, the cluster barrier + DSMEM reads add ~2 us) and
+  // cluster kernels overlap less under programmatic dependent launch.  Kept for the next round's persistent design.
+  static const bool want_fused = getenv("MGV_FUSED_DECODE") != nullptr;
+  const bool fused = want_fused && B <= 64 && (C / 64) % 8 == 0 && (C / 64) / 8 <= 2 && (4 * C / 64) % 16 == 0 &&
+                     (4 * C / 64) / 16 <= 4;
+  if (fused) {
+    for (int l = 0; l < g->L; ++l) {
+      const GptLayer& w = g->layers[l];
+      MGV_TRY(gemm_decode_ln(w.wqkv, 3 * C, C, g->dx, B, w.ln1_w, w.ln1_b, w.bqkv, g->dqkv32, 3 * C, 8, g->pdl, s));
+      MGV_TRY(gpt_attention_decode(g->dqkv32, B, g->nh, g->d_state, g->kcache(l), g->vcache(l), g->Tmax, g->dy,
+                                   (l == g->L - 1) ? att_out : nullptr, att_T, true, g->dh32,
+                                   static_cast<long long>(B) * 4 * C, s, g->pdl));
+      MGV_TRY(decode_gemm(g, g->dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, g->dx, g->dx, s));
+      MGV_TRY(gemm_decode_ln(w.wfc1, 4 * C, C, g->dx, B, w.ln2_w, w.ln2_b, w.bfc1, g->dh32, 4 * C, 8, g->pdl, s));
+      MGV_TRY(gemm_decode_gelu(w.wfc2, C, 4 * C, g->dh32, B, w.bfc2, g->dx, C, 16, g->pdl, s));
+      g->launches += 4;
+    }
+    MGV_TRY(gemm_decode_ln(g->whead, g->V, C, g->dx, B, g->lnf_w, g->lnf_b, nullptr, g->dlogits, g->V, 8, g->pdl, s));
+    MGV_TRY(gpt_sample_step(sa, s, g->pdl));
+    g->launches += 2;
+    return MGV_OK;
+  }
   const bool qs = tl.qkv_split > 1, fs = tl.fc1_split > 1;
   for (int l = 0; l < g->L; ++l) {
     const GptLayer& w = g->layers[l];
     MGV_TRY(gpt_layernorm(g->dx, w.ln1_w, w.ln1_b, B, C, g->dln, nullptr, 0, s, g->pdl));
     MGV_TRY(decode_gemm(g, g->dln, w.wqkv, w.bqkv, B, 3 * C, C, tl.qkv_split, EPI_F32, g->dqkv32, nullptr, s));
     MGV_TRY(gpt_attention_decode(g->dqkv32, B, g->nh, g->d_state, g->kcache(l), g->vcache(l), g->Tmax, g->dy,
-                                 (l == g->L - 1) ? att_out : nullptr, att_T, qs, s, g->pdl));
+                                 (l == g->L - 1) ? att_out : nullptr, att_T, qs, nullptr, 0, s, g->pdl));
     MGV_TRY(decode_gemm(g, g->dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, g->dx, g->dx, s));
     MGV_TRY(gpt_layernorm(g->dx, w.ln2_w, w.ln2_b, B, C, g->dln, nullptr, 0, s, g->pdl));
     if (fs) {
-      // (a "last split CTA applies GELU" finisher inside the FC1 kernel was measured slower than this tiny
-      //  elementwise kernel: 1287 vs 1111 us per position)
       MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_split, EPI_F32, g->dh32, nullptr, s));
       MGV_TRY(gpt_gelu_bf16(g->dh32, static_cast<long long>(B) * 4 * C, g->dh, true, s, g->pdl));
       g->launches += 1;

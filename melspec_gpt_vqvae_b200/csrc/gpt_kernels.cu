@@ -314,7 +314,8 @@ constexpr int AD_PASS = AD_KG * AD_KPP;   // 64 keys per pass
 __global__ void __launch_bounds__(AD_THREADS, 7)
 attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ pos_ptr,
                    __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache, int Tmax,
-                   __nv_bfloat16* __restrict__ y, float* __restrict__ att_rows, int Tatt, int zero_consumed) {
+                   __nv_bfloat16* __restrict__ y, float* __restrict__ att_rows, int Tatt, int zero_consumed,
+                   float* __restrict__ zero_buf, int zero_per_cta) {
   pdl_launch_dependents();
   __shared__ __align__(16) float sq[GPT_HEAD_DIM];
   __shared__ __align__(16) __nv_bfloat16 sk[GPT_HEAD_DIM];
@@ -346,6 +347,10 @@ attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ po
   uint4 b0[AD_KPP], b1[AD_KPP];
   load_rows(kc, nullptr, 0, b0);
   pdl_wait();
+  // clear this CTA's slice of the FC1 split-K accumulator: its last reader (the previous layer's FC2) has
+  // completed and the next writer (this layer's FC1) runs after this kernel
+  if (zero_buf)
+    for (int i = t; i < zero_per_cta; i += AD_THREADS) zero_buf[static_cast<long long>(blockIdx.x) * zero_per_cta + i] = 0.f;
   if (t < GPT_HEAD_DIM) {
     float* base = qkv32 + static_cast<long long>(b) * 3 * C + h * GPT_HEAD_DIM + t;
     // q is rounded to bf16 like the prefill path (which stores q,k,v as bf16)
@@ -709,12 +714,15 @@ int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_
 
 int gpt_attention_decode(float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
                          __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, bool zero_consumed,
-                         cudaStream_t s, bool pdl) {
+                         float* zero_buf, long long zero_count, cudaStream_t s, bool pdl) {
+  MGV_REQUIRE(zero_buf == nullptr || (B > 0 && zero_count % (static_cast<long long>(B) * nh) == 0),
+              "attention: zero_count must be a multiple of the CTA count");
   MGV_REQUIRE(Tmax <= GPT_MAX_T, "attention: Tmax=%d exceeds %d", Tmax, GPT_MAX_T);
   if (B == 0) return MGV_OK;
   LaunchCfg lc(dim3(B * nh), dim3(AD_THREADS), 0, s, pdl);
+  const int zero_per_cta = zero_buf ? static_cast<int>(zero_count / (static_cast<long long>(B) * nh)) : 0;
   MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_kernel, qkv32, nh, pos_ptr, kcache, vcache, Tmax, y, att_rows,
-                                    Tatt, zero_consumed ? 1 : 0));
+                                    Tatt, zero_consumed ? 1 : 0, zero_buf, zero_per_cta));
   return MGV_OK;
 }
 

@@ -29,9 +29,10 @@ int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_
 // One decode position: q,k,v fp32 [B, 3C] for position *pos_ptr; appends k,v to the cache and
 // attends over positions 0..pos.  att_rows (optional): fp32 [B, nh, Tatt, Tatt] pre-zeroed; entries 0..pos of row pos are written.
 // zero_consumed: the q,k,v accumulators are cleared after they are read (ready for the next split-K reduction).
+// zero_buf / zero_count: optional second fp32 buffer cleared cooperatively (the FC1 accumulator in the fused decode path).
 int gpt_attention_decode(float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
                          __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, bool zero_consumed,
-                         cudaStream_t s, bool pdl);
+                         float* zero_buf, long long zero_count, cudaStream_t s, bool pdl);
 
 // h = gelu_erf(h32) as bf16 (split-K FC1 path)
 int gpt_gelu_bf16(float* h32, long long n, __nv_bfloat16* out, bool zero_consumed, cudaStream_t s, bool pdl);

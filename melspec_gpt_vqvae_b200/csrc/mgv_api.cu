@@ -256,6 +256,16 @@ int mgv_test_gemm_swapab(int impl, const void* W, const void* X, int M, int N, i
   MGV_API_END
 }
 
+int mgv_test_gemm_fused(int mode, const void* W, const float* src, int Nw, int B, int K, const float* gamma,
+                        const float* beta, const float* bias, float* out, int split_k, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  MGV_TRY(check_device());
+  if (mode == 0)
+    return gemm_decode_gelu(W, Nw, K, src, B, bias, out, Nw, split_k, false, static_cast<cudaStream_t>(stream));
+  return gemm_decode_ln(W, Nw, K, src, B, gamma, beta, bias, out, Nw, split_k, false, static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
+
 int mgv_test_conv3x3(int impl, const void* x, const void* w, const float* bias, int n_img, int Hin, int Win, int Cin,
                      int Cout, int stride, void* out, const void* resid, mgv_stream_t stream) {
   MGV_API_BEGIN

@@ -79,6 +79,33 @@ def test_gemm_swapab_vs_torch(M, N, K, bn, split, epi):
     assert (out.float() - ref).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("mode,Nw,B,K,split", [
+    (0, 1024, 64, 4096, 16), (0, 1024, 5, 4096, 16), (0, 128, 64, 256, 1),
+    (1, 3072, 64, 1024, 8), (1, 4096, 64, 1024, 8), (1, 128, 64, 1024, 8), (1, 3072, 3, 1024, 8), (1, 256, 64, 128, 1),
+])
+def test_fused_decode_gemm(mode, Nw, B, K, split):
+    """decode GEMMs with the activation operand produced in-kernel: GELU(fp32 src) or LayerNorm(fp32 x) (cluster stats)."""
+    torch.manual_seed(Nw + B + K + mode)
+    W = (torch.randn(Nw, K, device="cuda") * 0.05).bfloat16()
+    src = torch.randn(B, K, device="cuda") * (1.0 if mode == 0 else 2.0) + (0.0 if mode == 0 else 0.3)
+    gamma = 1 + 0.1 * torch.randn(K, device="cuda")
+    beta = 0.1 * torch.randn(K, device="cuda")
+    bias = torch.randn(Nw, device="cuda")
+    init = torch.randn(B, Nw, device="cuda")
+    out = init.clone()
+    if mode == 0:
+        act = torch.nn.functional.gelu(src)
+    else:
+        act = torch.nn.functional.layer_norm(src, (K,), gamma, beta, 1e-5)
+    ref = init + act.bfloat16().float() @ W.float().t() + bias
+    _lib.check(_lib.load().mgv_test_gemm_fused(mode, _lib.ptr(W), _lib.ptr(src), Nw, B, K, _lib.ptr(gamma), _lib.ptr(beta),
+                                               _lib.ptr(bias), _lib.ptr(out), split, S0))
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    err = (out - ref).abs().max().item()
+    assert err <= 4e-3 * scale, "max err %.3e (scale %.3e)" % (err, scale)
+
+
 @pytest.mark.parametrize("n,H,W,Cin,Cout,stride,resid", [
     (2, 5, 53, 256, 512, 1, False), (2, 10, 106, 512, 512, 1, True), (1, 40, 424, 128, 128, 1, False),
     (1, 80, 848, 128, 128, 1, True), (2, 80, 848, 128, 128, 2, False), (2, 10, 106, 256, 256, 2, False),
