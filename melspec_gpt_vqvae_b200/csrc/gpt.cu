@@ -7,6 +7,7 @@
 #include "gemm_tc.cuh"
 #include "gpt_kernels.cuh"
 #include "gpt.cuh"
+#include "gpt_decode_program.cuh"
 
 namespace mgv {
 
@@ -69,7 +70,8 @@ struct Gpt {
   int dec_B = 0;  // decode batch capacity
   float *dx = nullptr, *dqkv32 = nullptr, *dh32 = nullptr, *dlogits = nullptr;
   __nv_bfloat16 *dln = nullptr, *dy = nullptr, *dh = nullptr, *kv = nullptr;
-  int* d_state = nullptr;  // [0]=pos, [1]=done counter, [2]=err flag, [4..5]=Philox seed (u64)
+  // [2]=err flag, [4..5]=Philox seed (u64), [8+2c]=position of sequence group c, [9+2c]=its done counter
+  int* d_state = nullptr;
   long long* dtokens = nullptr;  // [dec_B, block_size] token buffer the sampler writes (stable address for the graph)
   // cached decode-step graph (valid while the key matches and the workspaces are not reallocated)
   cudaGraph_t graph = nullptr;
@@ -77,6 +79,24 @@ struct Gpt {
   struct { int B, m, top_k, do_sample; float temperature; long long per_step; } graph_key = {0, 0, 0, 0, 0.f, 0};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // The decode step of one position is a chain of dependent ~4 us kernels that leaves most of the GPU idle, so the
+  // B sequences are split into `groups` independent groups whose chains run concurrently (parallel branches of the
+  // step graph) and fill each other's bubbles.  Rows of different sequences never interact, so results do not change.
+  static constexpr int MAX_GROUPS = 8;
+  int groups = 1;   // MGV_DECODE_GROUPS: measured 935 (2 groups) vs 1016 us per position, but every chain still pays the
+                    // full per-stage latency, and the default stays one group (deterministic launch order, simpler graph)
+  // Stage-program decode path (gpt_decode_program.cu, opt-in with MGV_DECODE_PROGRAM=1): per block one persistent
+  // kernel runs proj -> LN2 -> FC1+GELU -> FC2 -> LN1' -> QKV' with grid barriers instead of kernel boundaries.
+  // Correct (same tests), measured slower than the PDL chain (1215 vs 1016 us per position): see DESIGN.md section 7.
+  bool use_program = false;
+  DecStage* d_prog = nullptr;
+  CUtensorMap* d_maps = nullptr;
+  unsigned int* d_counters = nullptr;
+  unsigned long long* d_trace = nullptr;           // MGV_DP_TRACE=1: per-kernel stage timestamps (diagnostics)
+  int prog_B = 0;                                  // batch the program was built for (0 = none)
+  std::vector<std::pair<int, int>> prog_ranges;    // stage range of each program kernel of one position
+  cudaStream_t gstream[MAX_GROUPS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {};
   bool pdl = false;
   DecodeTiles tiles;
   long long launches = 0;  // kernels launched by the last forward / generate call
@@ -152,6 +172,7 @@ int ensure_decode_ws(Gpt* g, int B) {
   cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
   cudaFree(g->kv); cudaFree(g->dlogits); cudaFree(g->dtokens);
   g->dtokens = nullptr;
+  g->prog_B = 0;
   if (g->graph_exec) { cudaGraphExecDestroy(g->graph_exec); g->graph_exec = nullptr; }
   if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }
   g->dx = g->dqkv32 = g->dh32 = g->dlogits = nullptr;
@@ -267,11 +288,20 @@ int gpt_create(const GptConfig* cfg, Gpt** out) {
   carve_params(g, static_cast<char*>(g->slab), &total);
   g->n_tensors = 6 + 12 * g->L;
   g->loaded.assign(g->n_tensors, 0);
-  cudaMalloc(&g->d_state, 8 * sizeof(int));
-  cudaMemset(g->d_state, 0, 8 * sizeof(int));
+  cudaMalloc(&g->d_state, 32 * sizeof(int));
+  cudaMemset(g->d_state, 0, 32 * sizeof(int));
   cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&g->ev_in, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&g->ev_out, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
+  for (int c = 1; c < Gpt::MAX_GROUPS; ++c) {
+    cudaStreamCreateWithFlags(&g->gstream[c], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&g->ev_join[c], cudaEventDisableTiming);
+  }
+  const char* pe = getenv("MGV_DECODE_PROGRAM");
+  if (pe) g->use_program = atoi(pe) != 0;
+  const char* ge = getenv("MGV_DECODE_GROUPS");
+  if (ge && atoi(ge) >= 1 && atoi(ge) <= Gpt::MAX_GROUPS) g->groups = atoi(ge);
   const char* e = getenv("MGV_PDL");
   g->pdl = e ? atoi(e) != 0 : true;   // programmatic dependent launch between the decode-step kernels
   const char* tl = getenv("MGV_DECODE_SPLITS");
@@ -299,9 +329,15 @@ int gpt_destroy(Gpt* g) {
   if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
   if (g->graph) cudaGraphDestroy(g->graph);
   cudaFree(g->d_state);
+  cudaFree(g->d_prog); cudaFree(g->d_maps); cudaFree(g->d_counters); cudaFree(g->d_trace);
   if (g->stream) cudaStreamDestroy(g->stream);
   if (g->ev_in) cudaEventDestroy(g->ev_in);
   if (g->ev_out) cudaEventDestroy(g->ev_out);
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  for (int c = 1; c < Gpt::MAX_GROUPS; ++c) {
+    if (g->gstream[c]) cudaStreamDestroy(g->gstream[c]);
+    if (g->ev_join[c]) cudaEventDestroy(g->ev_join[c]);
+  }
   delete g;
   return MGV_OK;
 }
@@ -411,15 +447,17 @@ namespace {
 
 int decode_gemm(Gpt* g, const __nv_bfloat16* X, const __nv_bfloat16* W, const float* bias, int B, int N, int K,
                 int split, int epi_direct, void* out, const void* resid, cudaStream_t s) {
-  // swap-AB: the weights are the 128-row MMA operand, the B batch rows are the MMA N dimension
   GemmArgs a;
   a.stream = s;
   a.pdl = g->pdl;
   a.weights_evict_first = true;
-  a.transpose_out = true;
-  a.A = W; a.B = X; a.M = N; a.N = B; a.K = K;
   a.bias = bias;
   a.out = out;
+  // swap-AB: the weights are the 128-row MMA operand, the B batch rows are the MMA N dimension.  (Measured
+  // alternatives, both slower: sequences as the M rows with 16-byte vector reductions, 1144 vs 1016 us per position --
+  // a reduction costs per byte, not per instruction; activation tile staged with plain loads instead of TMA, 1025 us.)
+  a.transpose_out = true;
+  a.A = W; a.B = X; a.M = N; a.N = B; a.K = K;
   a.bn = B <= 32 ? 32 : (B <= 64 ? 64 : (B <= 128 ? 128 : 256));
   if (split > 1) {
     a.epi = EPI_F32_ATOMIC;
@@ -432,10 +470,21 @@ int decode_gemm(Gpt* g, const __nv_bfloat16* X, const __nv_bfloat16* W, const fl
   return gemm_bf16_tc(a);
 }
 
-// one decode position for all B sequences (enqueued on s; position read from g->d_state[0])
-int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int att_T, cudaStream_t s) {
+// one decode position for the B sequences of one group, rows [b0, b0+B) of the batch (enqueued on s; position
+// read from sa.pos_ptr)
+int enqueue_group_step(Gpt* g, int b0, int B, const SampleArgs& sa, float* att_out, int att_T, cudaStream_t s) {
   const int C = g->C;
   const DecodeTiles& tl = g->tiles;
+  const size_t r0 = static_cast<size_t>(b0);
+  float* dx = g->dx + r0 * C;
+  float* dqkv32 = g->dqkv32 + r0 * 3 * C;
+  float* dh32 = g->dh32 + r0 * 4 * C;
+  float* dlogits = g->dlogits + r0 * g->Vout;
+  __nv_bfloat16* dln = g->dln + r0 * C;
+  __nv_bfloat16* dy = g->dy + r0 * C;
+  __nv_bfloat16* dh = g->dh + r0 * 4 * C;
+  const size_t kv_off = r0 * g->nh * g->Tmax * GPT_HEAD_DIM;
+  if (att_out) att_out += r0 * g->nh * att_T * att_T;
   // Experimental fused path (MGV_FUSED_DECODE=1): LayerNorm applied inside the QKV / FC1 / head GEMMs (cluster-wide
   // row statistics over distributed shared memory) and GELU inside FC2 -> 5 dependent kernels per layer instead of
   // 8.  Measured SLOWER on B200 (1293 vs 1021 us per position): each fused kernel costs what its two parts cost
@@ -447,16 +496,16 @@ int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int
   if (fused) {
     for (int l = 0; l < g->L; ++l) {
       const GptLayer& w = g->layers[l];
-      MGV_TRY(gemm_decode_ln(w.wqkv, 3 * C, C, g->dx, B, w.ln1_w, w.ln1_b, w.bqkv, g->dqkv32, 3 * C, 8, g->pdl, s));
-      MGV_TRY(gpt_attention_decode(g->dqkv32, B, g->nh, g->d_state, g->kcache(l), g->vcache(l), g->Tmax, g->dy,
-                                   (l == g->L - 1) ? att_out : nullptr, att_T, true, g->dh32,
+      MGV_TRY(gemm_decode_ln(w.wqkv, 3 * C, C, dx, B, w.ln1_w, w.ln1_b, w.bqkv, dqkv32, 3 * C, 8, g->pdl, s));
+      MGV_TRY(gpt_attention_decode(dqkv32, B, g->nh, sa.pos_ptr, g->kcache(l) + kv_off, g->vcache(l) + kv_off, g->Tmax,
+                                   dy, (l == g->L - 1) ? att_out : nullptr, att_T, true, dh32,
                                    static_cast<long long>(B) * 4 * C, s, g->pdl));
-      MGV_TRY(decode_gemm(g, g->dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, g->dx, g->dx, s));
-      MGV_TRY(gemm_decode_ln(w.wfc1, 4 * C, C, g->dx, B, w.ln2_w, w.ln2_b, w.bfc1, g->dh32, 4 * C, 8, g->pdl, s));
-      MGV_TRY(gemm_decode_gelu(w.wfc2, C, 4 * C, g->dh32, B, w.bfc2, g->dx, C, 16, g->pdl, s));
+      MGV_TRY(decode_gemm(g, dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, dx, dx, s));
+      MGV_TRY(gemm_decode_ln(w.wfc1, 4 * C, C, dx, B, w.ln2_w, w.ln2_b, w.bfc1, dh32, 4 * C, 8, g->pdl, s));
+      MGV_TRY(gemm_decode_gelu(w.wfc2, C, 4 * C, dh32, B, w.bfc2, dx, C, 16, g->pdl, s));
       g->launches += 4;
     }
-    MGV_TRY(gemm_decode_ln(g->whead, g->V, C, g->dx, B, g->lnf_w, g->lnf_b, nullptr, g->dlogits, g->V, 8, g->pdl, s));
+    MGV_TRY(gemm_decode_ln(g->whead, g->V, C, dx, B, g->lnf_w, g->lnf_b, nullptr, dlogits, g->V, 8, g->pdl, s));
     MGV_TRY(gpt_sample_step(sa, s, g->pdl));
     g->launches += 2;
     return MGV_OK;
@@ -464,27 +513,177 @@ int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int
   const bool qs = tl.qkv_split > 1, fs = tl.fc1_split > 1;
   for (int l = 0; l < g->L; ++l) {
     const GptLayer& w = g->layers[l];
-    MGV_TRY(gpt_layernorm(g->dx, w.ln1_w, w.ln1_b, B, C, g->dln, nullptr, 0, s, g->pdl));
-    MGV_TRY(decode_gemm(g, g->dln, w.wqkv, w.bqkv, B, 3 * C, C, tl.qkv_split, EPI_F32, g->dqkv32, nullptr, s));
-    MGV_TRY(gpt_attention_decode(g->dqkv32, B, g->nh, g->d_state, g->kcache(l), g->vcache(l), g->Tmax, g->dy,
+    MGV_TRY(gpt_layernorm(dx, w.ln1_w, w.ln1_b, B, C, dln, nullptr, 0, s, g->pdl));
+    MGV_TRY(decode_gemm(g, dln, w.wqkv, w.bqkv, B, 3 * C, C, tl.qkv_split, EPI_F32, dqkv32, nullptr, s));
+    MGV_TRY(gpt_attention_decode(dqkv32, B, g->nh, sa.pos_ptr, g->kcache(l) + kv_off, g->vcache(l) + kv_off, g->Tmax, dy,
                                  (l == g->L - 1) ? att_out : nullptr, att_T, qs, nullptr, 0, s, g->pdl));
-    MGV_TRY(decode_gemm(g, g->dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, g->dx, g->dx, s));
-    MGV_TRY(gpt_layernorm(g->dx, w.ln2_w, w.ln2_b, B, C, g->dln, nullptr, 0, s, g->pdl));
+    MGV_TRY(decode_gemm(g, dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, dx, dx, s));
+    MGV_TRY(gpt_layernorm(dx, w.ln2_w, w.ln2_b, B, C, dln, nullptr, 0, s, g->pdl));
     if (fs) {
-      MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_split, EPI_F32, g->dh32, nullptr, s));
-      MGV_TRY(gpt_gelu_bf16(g->dh32, static_cast<long long>(B) * 4 * C, g->dh, true, s, g->pdl));
+      MGV_TRY(decode_gemm(g, dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_split, EPI_F32, dh32, nullptr, s));
+      MGV_TRY(gpt_gelu_bf16(dh32, static_cast<long long>(B) * 4 * C, dh, true, s, g->pdl));
       g->launches += 1;
     } else {
-      MGV_TRY(decode_gemm(g, g->dln, w.wfc1, w.bfc1, B, 4 * C, C, 1, EPI_BF16_GELU, g->dh, nullptr, s));
+      MGV_TRY(decode_gemm(g, dln, w.wfc1, w.bfc1, B, 4 * C, C, 1, EPI_BF16_GELU, dh, nullptr, s));
     }
-    MGV_TRY(decode_gemm(g, g->dh, w.wfc2, w.bfc2, B, C, 4 * C, tl.fc2_split, EPI_F32_RESID, g->dx, g->dx, s));
+    MGV_TRY(decode_gemm(g, dh, w.wfc2, w.bfc2, B, C, 4 * C, tl.fc2_split, EPI_F32_RESID, dx, dx, s));
     g->launches += 3;
   }
   // ln_f + head (minGPT.py:186-188) with the same kernels as the blocks, then the fused sampler
-  MGV_TRY(gpt_layernorm(g->dx, g->lnf_w, g->lnf_b, B, C, g->dln, nullptr, 0, s, g->pdl));
-  MGV_TRY(decode_gemm(g, g->dln, g->whead, nullptr, B, g->V, C, tl.head_split, EPI_F32, g->dlogits, nullptr, s));
+  MGV_TRY(gpt_layernorm(dx, g->lnf_w, g->lnf_b, B, C, dln, nullptr, 0, s, g->pdl));
+  MGV_TRY(decode_gemm(g, dln, g->whead, nullptr, B, g->V, C, tl.head_split, EPI_F32, dlogits, nullptr, s));
   MGV_TRY(gpt_sample_step(sa, s, g->pdl));
   g->launches += 2;
+  return MGV_OK;
+}
+
+// ---- stage-program path ------------------------------------------------------------------------------------
+bool program_gemm_shape(int n_feat, int K, int B, int n_ctas, int* ftiles, int* rhalves, int* splits) {
+  if (K % 64 != 0) return false;
+  const int nkb = K / 64;
+  *ftiles = (n_feat + 63) / 64;
+  *rhalves = (B + 31) / 32;
+  *splits = (nkb + DP_MAX_KB - 1) / DP_MAX_KB;
+  return *ftiles * *rhalves * *splits <= n_ctas;
+}
+
+bool program_eligible(const Gpt* g, int B) {
+  if (!g->use_program || B < 1 || B > 64 || g->C > 1024 || g->C % 64 != 0) return false;
+  const int n = num_sms();
+  int t, r, sp;
+  return program_gemm_shape(3 * g->C, g->C, B, n, &t, &r, &sp) && program_gemm_shape(g->C, g->C, B, n, &t, &r, &sp) &&
+         program_gemm_shape(4 * g->C, g->C, B, n, &t, &r, &sp) && program_gemm_shape(g->C, 4 * g->C, B, n, &t, &r, &sp) &&
+         program_gemm_shape(g->V, g->C, B, n, &t, &r, &sp);
+}
+
+// builds (or reuses) the device-side stage list and tensor-map table for batch B; not capturable (synchronous copies)
+int build_decode_program(Gpt* g, int B, cudaStream_t s) {
+  if (g->prog_B == B && g->d_prog) return MGV_OK;
+  const int C = g->C, L = g->L, n_ctas = num_sms();
+  std::vector<CUtensorMap> maps(3 + 4 * L + 1);
+  // activations: box = 64 k x 32 sequences; weights: box = 64 k x 64 rows
+  MGV_TRY(make_tmap_2d_bf16(&maps[0], g->dln, C, B, static_cast<uint64_t>(C) * 2, 64, 32));
+  MGV_TRY(make_tmap_2d_bf16(&maps[1], g->dy, C, B, static_cast<uint64_t>(C) * 2, 64, 32));
+  MGV_TRY(make_tmap_2d_bf16(&maps[2], g->dh, 4 * C, B, static_cast<uint64_t>(4 * C) * 2, 64, 32));
+  for (int l = 0; l < L; ++l) {
+    const GptLayer& w = g->layers[l];
+    MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * l + 0], w.wqkv, C, 3 * C, static_cast<uint64_t>(C) * 2, 64, 64));
+    MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * l + 1], w.wproj, C, C, static_cast<uint64_t>(C) * 2, 64, 64));
+    MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * l + 2], w.wfc1, C, 4 * C, static_cast<uint64_t>(C) * 2, 64, 64));
+    MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * l + 3], w.wfc2, 4 * C, C, static_cast<uint64_t>(4 * C) * 2, 64, 64));
+  }
+  MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * L], g->whead, C, g->V, static_cast<uint64_t>(C) * 2, 64, 64));
+
+  std::vector<DecStage> prog;
+  g->prog_ranges.clear();
+  auto ln = [&](const float* gamma, const float* beta) {
+    DecStage d;
+    memset(&d, 0, sizeof(d));
+    d.type = DST_LN; d.B = B; d.C = C;
+    d.x = g->dx; d.gamma = gamma; d.beta = beta; d.ln_out = g->dln;
+    prog.push_back(d);
+  };
+  auto gemm = [&](int map_w, int map_x, int n_feat, int K, int mode, const float* bias, void* out, long long ldo) -> int {
+    DecStage d;
+    memset(&d, 0, sizeof(d));
+    d.type = DST_GEMM; d.B = B; d.C = C;
+    d.map_w = map_w; d.map_x = map_x; d.n_feat = n_feat; d.nkb = K / 64;
+    MGV_REQUIRE(program_gemm_shape(n_feat, K, B, n_ctas, &d.ftiles, &d.rhalves, &d.splits),
+                "decode program: GEMM %dx%d does not fit", n_feat, K);
+    d.mode = (mode == DGM_ADD_F32 && d.splits > 1) ? DGM_RED_F32 : mode;
+    MGV_REQUIRE(d.splits == 1 || d.mode == DGM_RED_F32, "decode program: split-K GEMM %dx%d needs the reduction epilogue", n_feat, K);
+    d.bias = bias; d.out = out; d.ldo = ldo;
+    prog.push_back(d);
+    return MGV_OK;
+  };
+  // kernel 0: LN1 + QKV of block 0
+  ln(g->layers[0].ln1_w, g->layers[0].ln1_b);
+  MGV_TRY(gemm(3 + 0, 0, 3 * C, C, DGM_STORE_F32, g->layers[0].bqkv, g->dqkv32, 3 * C));
+  g->prog_ranges.push_back({0, 2});
+  for (int l = 0; l < L; ++l) {
+    const GptLayer& w = g->layers[l];
+    const int begin = static_cast<int>(prog.size());
+    MGV_TRY(gemm(3 + 4 * l + 1, 1, C, C, DGM_ADD_F32, w.bproj, g->dx, C));                 // x += proj(y)
+    ln(w.ln2_w, w.ln2_b);
+    MGV_TRY(gemm(3 + 4 * l + 2, 0, 4 * C, C, DGM_GELU_BF16, w.bfc1, g->dh, 4 * C));        // h = gelu(fc1(ln2(x)))
+    MGV_TRY(gemm(3 + 4 * l + 3, 2, C, 4 * C, DGM_ADD_F32, w.bfc2, g->dx, C));              // x += fc2(h)
+    if (l + 1 < L) {
+      const GptLayer& nx = g->layers[l + 1];
+      ln(nx.ln1_w, nx.ln1_b);
+      MGV_TRY(gemm(3 + 4 * (l + 1) + 0, 0, 3 * C, C, DGM_STORE_F32, nx.bqkv, g->dqkv32, 3 * C));
+    } else {
+      ln(g->lnf_w, g->lnf_b);
+      MGV_TRY(gemm(3 + 4 * L, 0, g->V, C, DGM_STORE_F32, nullptr, g->dlogits, g->V));
+    }
+    g->prog_ranges.push_back({begin, static_cast<int>(prog.size())});
+  }
+  cudaFree(g->d_prog); cudaFree(g->d_maps);
+  g->d_prog = nullptr; g->d_maps = nullptr;
+  g->prog_B = 0;
+  MGV_CHECK_CUDA(cudaMalloc(&g->d_prog, prog.size() * sizeof(DecStage)));
+  MGV_CHECK_CUDA(cudaMalloc(&g->d_maps, maps.size() * sizeof(CUtensorMap)));
+  if (!g->d_counters) MGV_CHECK_CUDA(cudaMalloc(&g->d_counters, 256 * sizeof(unsigned int)));
+  if (!g->d_trace && getenv("MGV_DP_TRACE")) {
+    MGV_CHECK_CUDA(cudaMalloc(&g->d_trace, 256 * DP_TRACE_WORDS * 8));
+    MGV_CHECK_CUDA(cudaMemset(g->d_trace, 0, 256 * DP_TRACE_WORDS * 8));
+  }
+  MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_prog, prog.data(), prog.size() * sizeof(DecStage), cudaMemcpyHostToDevice, s));
+  MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s));
+  MGV_CHECK_CUDA(cudaStreamSynchronize(s));
+  g->prog_B = B;
+  return MGV_OK;
+}
+
+// one decode position through the stage program: L+1 persistent kernels interleaved with the L attention kernels
+int enqueue_program_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int att_T, cudaStream_t s) {
+  const int L = g->L, n_ctas = num_sms();
+  MGV_REQUIRE(g->prog_B == B && static_cast<int>(g->prog_ranges.size()) == L + 1 && L + 1 <= 256, "decode program not built");
+  MGV_CHECK_CUDA(cudaMemsetAsync(g->d_counters, 0, (L + 1) * sizeof(unsigned int), s));
+  MGV_TRY(decode_program_launch(g->d_prog, g->prog_ranges[0].first, g->prog_ranges[0].second, g->d_maps, g->d_counters,
+                                n_ctas, g->pdl, s, g->d_trace));
+  for (int l = 0; l < L; ++l) {
+    MGV_TRY(gpt_attention_decode(g->dqkv32, B, g->nh, sa.pos_ptr, g->kcache(l), g->vcache(l), g->Tmax, g->dy,
+                                 (l == L - 1) ? att_out : nullptr, att_T, false, nullptr, 0, s, g->pdl));
+    MGV_TRY(decode_program_launch(g->d_prog, g->prog_ranges[l + 1].first, g->prog_ranges[l + 1].second, g->d_maps,
+                                  g->d_counters + l + 1, n_ctas, g->pdl, s,
+                                  g->d_trace ? g->d_trace + (l + 1) * DP_TRACE_WORDS : nullptr));
+  }
+  MGV_TRY(gpt_sample_step(sa, s, g->pdl));
+  g->launches += 2 * L + 2;
+  return MGV_OK;
+}
+
+int decode_groups(const Gpt* g, int B) {
+  int n = g->groups;
+  while (n > 1 && B / n < 8) n >>= 1;   // tiny batches: one chain
+  return n < 1 ? 1 : n;
+}
+
+// one decode position for all B sequences: the sequence groups fork from s, run their chains on their own
+// streams and join back (inside a stream capture this becomes parallel branches of the step graph)
+int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa0, float* att_out, int att_T, cudaStream_t s) {
+  const int ng = decode_groups(g, B);
+  if (ng == 1 && g->prog_B == B && program_eligible(g, B)) return enqueue_program_step(g, B, sa0, att_out, att_T, s);
+  if (ng > 1) MGV_CHECK_CUDA(cudaEventRecord(g->ev_fork, s));
+  int b0 = 0;
+  for (int c = 0; c < ng; ++c) {
+    const int Bc = B / ng + (c < B % ng ? 1 : 0);
+    cudaStream_t cs = c == 0 ? s : g->gstream[c];
+    if (c > 0) MGV_CHECK_CUDA(cudaStreamWaitEvent(cs, g->ev_fork, 0));
+    SampleArgs sa = sa0;
+    sa.B = Bc;
+    sa.row0 = b0;
+    sa.logits_acc = sa0.logits_acc + static_cast<size_t>(b0) * g->V;
+    sa.tokens = sa0.tokens + static_cast<size_t>(b0) * sa0.tokens_ld;
+    sa.x_next = sa0.x_next + static_cast<size_t>(b0) * g->C;
+    sa.pos_ptr = g->d_state + 8 + 2 * c;
+    sa.done_counter = reinterpret_cast<unsigned int*>(g->d_state + 9 + 2 * c);
+    const int rc = enqueue_group_step(g, b0, Bc, sa, att_out, att_T, cs);
+    if (rc != MGV_OK) return rc;
+    if (c > 0) MGV_CHECK_CUDA(cudaEventRecord(g->ev_join[c], cs));
+    b0 += Bc;
+  }
+  for (int c = 1; c < ng; ++c) MGV_CHECK_CUDA(cudaStreamWaitEvent(s, g->ev_join[c], 0));
   return MGV_OK;
 }
 
@@ -547,8 +746,9 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   MGV_CHECK_CUDA(cudaMemsetAsync(g->dqkv32, 0, static_cast<size_t>(B) * 3 * g->C * 4, s));
   MGV_CHECK_CUDA(cudaMemsetAsync(g->dh32, 0, static_cast<size_t>(B) * 4 * g->C * 4, s));
   MGV_CHECK_CUDA(cudaMemsetAsync(g->dlogits, 0, static_cast<size_t>(B) * g->Vout * 4, s));
-  const int init_state[2] = {T0 - 1, 0};
-  MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state, init_state, 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+  int init_state[2 * Gpt::MAX_GROUPS];
+  for (int c = 0; c < Gpt::MAX_GROUPS; ++c) { init_state[2 * c] = T0 - 1; init_state[2 * c + 1] = 0; }
+  MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state + 8, init_state, sizeof(init_state), cudaMemcpyHostToDevice, s));
   MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state + 4, &seed, sizeof(seed), cudaMemcpyHostToDevice, s));
 
   SampleArgs sa;
@@ -557,12 +757,14 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   sa.B = B; sa.C = g->C; sa.V = g->V;
   sa.temperature = temperature; sa.top_k = top_k; sa.do_sample = do_sample;
   sa.seed_ptr = reinterpret_cast<const unsigned long long*>(g->d_state + 4);
-  sa.pos_ptr = g->d_state;
+  sa.pos_ptr = g->d_state + 8;
   sa.tokens = g->dtokens; sa.tokens_ld = tld; sa.m = m;
   sa.tok_emb = g->tok_emb; sa.pos_emb = g->pos_emb; sa.block_size = g->cfg.block_size;
   sa.x_next = g->dx; sa.logits_out = nullptr;
-  sa.done_counter = reinterpret_cast<unsigned int*>(g->d_state + 1);
+  sa.done_counter = reinterpret_cast<unsigned int*>(g->d_state + 9);
 
+  if (decode_groups(g, B) == 1 && program_eligible(g, B)) MGV_TRY(build_decode_program(g, B, s));
+  else g->prog_B = 0;
   cudaGraph_t tmp_graph = nullptr;
   cudaGraphExec_t tmp_exec = nullptr;
   if (use_graph) {
@@ -618,6 +820,18 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   const cudaError_t e1 = cudaEventRecord(g->ev_out, s);
   const cudaError_t e2 = cudaStreamWaitEvent(caller, g->ev_out, 0);
   const int rc = read_err_flag(g, s, "gpt_generate");  // synchronises s
+  if (g->d_trace && g->prog_B == B) {   // diagnostics: stage timeline of the last position (CTA 0)
+    std::vector<unsigned long long> tr(static_cast<size_t>(g->L + 1) * DP_TRACE_WORDS);
+    if (cudaMemcpy(tr.data(), g->d_trace, tr.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      const unsigned long long t0 = tr[0];
+      for (int k = 0; k <= g->L && k < 4; ++k) {
+        fprintf(stderr, "[dp-trace] kernel %d:", k);
+        for (int i = 0; i < DP_TRACE_WORDS; ++i)
+          fprintf(stderr, " %.2f", tr[k * DP_TRACE_WORDS + i] ? (static_cast<double>(tr[k * DP_TRACE_WORDS + i]) - static_cast<double>(t0)) * 1e-3 : 0.0);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   if (tmp_exec) cudaGraphExecDestroy(tmp_exec);
   if (tmp_graph) cudaGraphDestroy(tmp_graph);
   MGV_CHECK_CUDA(e0);

@@ -588,7 +588,7 @@ sample_step_kernel(const SampleArgs a) {
         const float up = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += up;
       }
-      const float u = philox_uniform(*a.seed_ptr, static_cast<uint32_t>(pos), static_cast<uint32_t>(b));
+      const float u = philox_uniform(*a.seed_ptr, static_cast<uint32_t>(pos), static_cast<uint32_t>(a.row0 + b));
       const float target = u * __shfl_sync(0xffffffffu, incl, 31);
       const float excl = incl - mine;
       // first index whose cumulative probability exceeds the target

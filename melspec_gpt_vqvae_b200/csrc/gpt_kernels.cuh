@@ -40,6 +40,7 @@ int gpt_gelu_bf16(float* h32, long long n, __nv_bfloat16* out, bool zero_consume
 struct SampleArgs {
   float* logits_acc;       // [B, V] fp32: head logits of this position (split-K accumulator; cleared here after use)
   int B, C, V;
+  int row0;                // index of this group's first sequence in the whole batch (Philox counter = row0 + b)
   float temperature;
   int top_k;               // 0 = no top-k
   int do_sample;           // 0 = greedy (torch.topk(probs, 1)), 1 = multinomial

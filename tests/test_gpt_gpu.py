@@ -91,7 +91,13 @@ def _lit(cfg, sd):
     return lit.eval().to("cuda")
 
 
-def test_greedy_sample_vs_golden_and_kv_cache_consistency():
+# the decode loop has three schedules: the default PDL kernel chain, two concurrent sequence
+# groups, and the persistent stage-program kernels; the environment is read when the handle is created
+@pytest.mark.parametrize("decode_env", [{}, {"MGV_DECODE_GROUPS": "2"}, {"MGV_DECODE_PROGRAM": "1"}],
+                         ids=["pdl_chain", "two_groups", "stage_program"])
+def test_greedy_sample_vs_golden_and_kv_cache_consistency(decode_env, monkeypatch):
+    for k, v in decode_env.items():
+        monkeypatch.setenv(k, v)
     g = golden("gpt_small_greedy.npz")
     sd = synthetic.synthetic_gpt_state_dict(GPT_SMALL, seed=101, perturb=True)
     sd["head.weight"] = sd["head.weight"] * 8.0

@@ -29,11 +29,11 @@ def kname(e):
     m = re.search(r"(gemm_tc_kernel<\d+>|[a-z_0-9]+_kernel)", e["name"])
     n = m.group(1) if m else e["name"][:30]
     g = e.get("args", {}).get("grid", "")
-    return "%s grid=%s" % (n, g)
+    return "%s grid=%s stream=%s" % (n, g, e.get("args", {}).get("stream", ""))
 print("kernels traced:", len(ev))
 dur = collections.defaultdict(list); gap = collections.defaultdict(list)
 for i, e in enumerate(ev):
-    name = kname(e)
+    name = kname(e).split(" stream=")[0]
     dur[name].append(e["dur"])
     if i > 0:
         gap[name].append(e["ts"] - (ev[i - 1]["ts"] + ev[i - 1]["dur"]))
@@ -42,6 +42,16 @@ print("span %.1f us over %d positions = %.1f us/position" % (tot, steps, tot / s
 for k in dur:
     g = gap[k]
     print("%-42s n=%5d dur avg %.2f us (sum %.0f)  gap-before avg %.2f us (sum %.0f)" % (k, len(dur[k]), sum(dur[k]) / len(dur[k]), sum(dur[k]), sum(g) / max(len(g), 1), sum(g)))
+busy = 0.0; cur_s = None; cur_e = None
+for e in ev:
+    a, b = e["ts"], e["ts"] + e["dur"]
+    if cur_e is None or a > cur_e:
+        if cur_e is not None: busy += cur_e - cur_s
+        cur_s, cur_e = a, b
+    else:
+        cur_e = max(cur_e, b)
+busy += cur_e - cur_s
+print("union of kernel intervals %.0f us of span %.0f us ; sum of durations %.0f us" % (busy, tot, sum(sum(v) for v in dur.values())))
 # one layer of the last position in detail
 last = ev[-60:-30]
 t0 = last[0]["ts"]
