@@ -117,6 +117,14 @@ int mgv_gpt_generate(mgv_gpt_t* g, const int64_t* x0, int B, int t0, const float
                      int m, int steps, float temperature, int do_sample, int top_k, uint64_t seed,
                      int64_t* x_out, float* att_out, int use_graph, mgv_stream_t stream);
 
+/* Per-row cross entropy, loss_out[r] = logsumexp(logits[r, :V]) - logits[r, targets[r]]:
+ * F.cross_entropy in GPT.forward(targets=...) (transformer/minGPT.py:195-197, mean taken by the caller) and
+ * nn.CrossEntropyLoss(weight=ones, reduction='none') in GPTDecoder.reconstruct_error (transformer/decoders.py:21,64-68).
+ *   logits: fp32 (rows, V) contiguous;  targets: int64 (rows,);  loss_out: fp32 (rows,).
+ * A target outside [0, V) fails with MGV_ERR_INVALID (torch raises an index error).  Synchronises. */
+int mgv_gpt_cross_entropy(mgv_gpt_t* g, const float* logits, const int64_t* targets, int64_t rows, int V, float* loss_out,
+                          mgv_stream_t stream);
+
 /* number of kernels libmgv launched in the last forward / generate call on this handle */
 int64_t mgv_gpt_last_launches(const mgv_gpt_t* g);
 

@@ -250,7 +250,7 @@ int read_err_flag(Gpt* g, cudaStream_t s, const char* what) {
   MGV_CHECK_CUDA(cudaStreamSynchronize(s));
   if (flag != 0) {
     MGV_CHECK_CUDA(cudaMemsetAsync(g->d_state + 2, 0, sizeof(int), s));
-    set_error("%s: %s index out of range", what, flag == 1 ? "class" : "token");
+    set_error("%s: %s index out of range", what, flag == 1 ? "class" : (flag == 2 ? "token / target" : "token"));
     return MGV_ERR_INVALID;
   }
   return MGV_OK;
@@ -842,6 +842,17 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   MGV_CHECK_CUDA(e1);
   MGV_CHECK_CUDA(e2);
   return rc;
+}
+
+// per-row cross entropy of fp32 logits [rows, V] against int64 targets (minGPT.py:197, decoders.py:64-68)
+int gpt_cross_entropy(Gpt* g, const float* logits, const long long* targets, long long rows, int V, float* loss,
+                      cudaStream_t s) {
+  MGV_REQUIRE(g, "gpt_cross_entropy: null handle");
+  MGV_REQUIRE(rows >= 0, "gpt_cross_entropy: negative rows");
+  if (rows == 0) return MGV_OK;
+  MGV_TRY(gpt_ce_rows(logits, targets, rows, V, V, loss, g->d_state + 2, s));
+  g->launches = 1;
+  return read_err_flag(g, s, "gpt_cross_entropy");
 }
 
 long long gpt_last_launches(const Gpt* g) { return g ? g->launches : 0; }

@@ -25,6 +25,8 @@ int gpt_forward(Gpt* g, const long long* idx, int B, int t, const float* prefix_
 int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix_emb, const long long* cls, int m,
                  int steps, float temperature, int do_sample, int top_k, unsigned long long seed, long long* x_out,
                  float* att_out, int use_graph, cudaStream_t caller);
+int gpt_cross_entropy(Gpt* g, const float* logits, const long long* targets, long long rows, int V, float* loss,
+                      cudaStream_t s);
 long long gpt_last_launches(const Gpt* g);
 
 }  // namespace mgv

@@ -666,7 +666,46 @@ sample_step_kernel(const SampleArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ cross entropy per row
+// loss[r] = logsumexp(logits[r, :]) - logits[r, target[r]]  (F.cross_entropy / nn.CrossEntropyLoss with unit class
+// weights, reduction='none': transformer/minGPT.py:197, transformer/decoders.py:21,64-68).  One warp per row.
+__global__ void __launch_bounds__(128)
+ce_rows_kernel(const float* __restrict__ logits, const long long* __restrict__ targets, long long rows, int V,
+               long long ld, float* __restrict__ loss, int* __restrict__ err_flag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 4 + warp;
+  if (r >= rows) return;
+  const float* row = logits + r * ld;
+  float mx = -INFINITY;
+  for (int i = lane; i < V; i += 32) mx = fmaxf(mx, row[i]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < V; i += 32) sum += expf(row[i] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) {
+    const long long t = targets[r];
+    if (t < 0 || t >= V) {
+      *err_flag = 2;
+      loss[r] = NAN;
+    } else {
+      loss[r] = (mx + logf(sum)) - row[t];
+    }
+  }
+}
+
 }  // namespace
+
+int gpt_ce_rows(const float* logits, const long long* targets, long long rows, int V, long long ld, float* loss,
+                int* err_flag, cudaStream_t s) {
+  MGV_REQUIRE(logits && targets && loss && err_flag, "cross entropy: null");
+  MGV_REQUIRE(V >= 1 && ld >= V, "cross entropy: V=%d ld=%lld", V, ld);
+  if (rows == 0) return MGV_OK;
+  const long long blocks = (rows + 3) / 4;
+  MGV_REQUIRE(blocks <= 0x7fffffffLL, "cross entropy: too many rows");
+  ce_rows_kernel<<<static_cast<unsigned>(blocks), 128, 0, s>>>(logits, targets, rows, V, ld, loss, err_flag);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
 
 // ====================================================================== host wrappers
 int gpt_embed(const long long* idx, int B, int R, int p_off, int idx_ld, const float* prefix_emb, const long long* cls,

@@ -58,4 +58,8 @@ struct SampleArgs {
 };
 int gpt_sample_step(const SampleArgs& a, cudaStream_t s, bool pdl);
 
+// loss[r] = logsumexp(logits[r, :V]) - logits[r, targets[r]]; a target outside [0, V) sets *err_flag = 2
+int gpt_ce_rows(const float* logits, const long long* targets, long long rows, int V, long long ld, float* loss,
+                int* err_flag, cudaStream_t s);
+
 }  // namespace mgv

@@ -194,6 +194,13 @@ int mgv_gpt_generate(mgv_gpt_t* g, const int64_t* x0, int B, int t0, const float
                       reinterpret_cast<long long*>(x_out), att_out, use_graph, static_cast<cudaStream_t>(stream));
   MGV_API_END
 }
+int mgv_gpt_cross_entropy(mgv_gpt_t* g, const float* logits, const int64_t* targets, int64_t rows, int V, float* loss_out,
+                          mgv_stream_t stream) {
+  MGV_API_BEGIN
+  return gpt_cross_entropy(reinterpret_cast<Gpt*>(g), logits, reinterpret_cast<const long long*>(targets), rows, V, loss_out,
+                           static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
 int64_t mgv_gpt_last_launches(const mgv_gpt_t* g) { return gpt_last_launches(reinterpret_cast<const Gpt*>(g)); }
 
 int mgv_vqvae_create(int num_embeddings, int embedding_dim, mgv_vqvae_t** out) {

@@ -8,6 +8,7 @@ libmgv (include/mgv.h):
   GPT.forward / GPTClass.forward   -> mgv_gpt_forward   (bf16 tcgen05 GEMMs, fp32 accumulate)
   Lit_minGPT.sample                -> mgv_gpt_generate  (KV cache + CUDA-graph decode loop)
   Lit_minGPT.decode_to_img         -> code_reader + mgv_vqvae_decode_codes
+  GPT.forward(targets=...) loss    -> mgv_gpt_cross_entropy
 
 Inference (eval mode) only: the reference's training step is a "next" row (SURVEY.md
 section 8(f)).  No CPU fallback.
@@ -203,8 +204,25 @@ class GPT(nn.Module):
         logits, att = self._forward_impl(idx, embeddings, None)
         loss = None
         if targets is not None:
-            loss = F.cross_entropy(logits.view(-1, logits.size(-1)), targets.view(-1))
+            # F.cross_entropy (reference :197): mean over the targets that are not ignore_index (-100)
+            t = targets.reshape(-1)
+            keep = t != -100
+            rows = self.cross_entropy_rows(logits.view(-1, logits.size(-1)), t.masked_fill(~keep, 0))
+            loss = (rows * keep).sum() / keep.sum()
         return logits, loss, att
+
+    def cross_entropy_rows(self, logits2d, targets1d):
+        """per-row cross entropy (rows,) fp32 of fp32 logits (rows, V) -> mgv_gpt_cross_entropy"""
+        if not logits2d.is_cuda:
+            raise RuntimeError("cross_entropy_rows: logits are on %s; libmgv has no CPU path" % logits2d.device)
+        lg = logits2d.detach().to(torch.float32).contiguous()
+        t = targets1d.detach().to(device=lg.device, dtype=torch.int64).contiguous()
+        rows, V = lg.shape
+        assert t.numel() == rows, "cross_entropy_rows: %d targets for %d rows" % (t.numel(), rows)
+        out = torch.empty(rows, dtype=torch.float32, device=lg.device)
+        _lib.check(_lib.load().mgv_gpt_cross_entropy(self._handle(), _lib.ptr(lg), _lib.ptr(t), rows, V, _lib.ptr(out),
+                                                     _lib.stream_ptr()), "mgv_gpt_cross_entropy")
+        return out
 
     def last_launches(self):
         return int(_lib.load().mgv_gpt_last_launches(self._handle()))
@@ -356,7 +374,7 @@ class Lit_minGPT(_LitBase):
     def shared_step(self, batch, batch_idx):
         x, c = self.get_xc(batch)
         logits, target = self(x, c)
-        return F.cross_entropy(logits.reshape(-1, logits.size(-1)), target.reshape(-1))
+        return self.transformer.cross_entropy_rows(logits.reshape(-1, logits.size(-1)), target.reshape(-1)).mean()
 
     def validation_step(self, batch, batch_idx):
         loss = self.shared_step(batch, batch_idx)

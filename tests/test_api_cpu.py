@@ -121,3 +121,21 @@ def test_code_reader_host_logic():
     assert torch.equal(lit.get_x({"codes": codes}), lit.code_reader(codes.reshape(2, -1)))
     lg = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "topk.npz"))["logits"])
     assert torch.equal(lit.top_k_logits(lg, 100), torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "topk.npz"))["out100"]))
+
+
+def test_gpt_vae_dropin_state_dict_keys_match_reference():
+    """GPT_VAE drop-in registers exactly the reference's parameters / buffers (encoder.*, decoder.*, decoder.loss.weight)."""
+    import argparse
+    import os
+    import numpy as np
+    from melspec_gpt_vqvae_b200.transformer import GPTDecoder, GPTEncoder  # noqa: F401  (the reference's import surface)
+    from melspec_gpt_vqvae_b200.transformer.Lit_GPT_VAE import GPT_VAE
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gpt_vae_small.npz"))
+    args = argparse.Namespace(embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, fix_var=-1.0, device="cpu", vocab_size=128,
+                              block_size=265, n_layer=2, n_head=2, n_embd=128)
+    m = GPT_VAE(args)
+    ours = set(m.state_dict().keys())
+    ref = set(str(k) for k in g["state_dict_keys"])
+    masks = {k for k in ref if k.endswith("attn.mask")}      # derived from n_unmasked inside libmgv; optional buffer
+    assert ours - masks == ref - masks, (sorted(ours - ref)[:5], sorted(ref - masks - ours)[:5])
+    assert m.encoder.transformer.head.weight.shape == (256, 128) and m.decoder.transformer.pos_emb.shape == (1, 266, 128)

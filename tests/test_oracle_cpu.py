@@ -8,7 +8,8 @@ import torch
 
 from make_golden import GPT_SMALL, GPT_SMALL_UNMASKED, gpt_inputs, vq_inputs
 from melspec_gpt_vqvae_b200 import synthetic
-from oracle import gpt_oracle, vq_oracle, vqvae_oracle
+from make_golden_vae import GPT_VAE_SMALL, vae_inputs, vae_state_dicts
+from oracle import gpt_oracle, gpt_vae_oracle, vq_oracle, vqvae_oracle
 
 
 def load(golden_dir, name):
@@ -145,3 +146,30 @@ def test_vqvae_oracle(golden_dir):
     melin = torch.rand(1, 1, 80, 848, generator=gen) * 2 - 1
     z = vqvae_oracle.encode(sd, melin)
     np.testing.assert_allclose(z.numpy(), g["z"], rtol=1e-4, atol=1e-5)
+
+
+def test_gpt_vae_oracle_vs_reference_golden(golden_dir):
+    """GPTEncoder / GPTDecoder restatement against the unmodified reference classes' outputs."""
+    g = load(golden_dir, "gpt_vae_small.npz")
+    ecfg = gpt_vae_oracle.encoder_cfg(**GPT_VAE_SMALL)
+    dcfg = gpt_vae_oracle.decoder_cfg(**GPT_VAE_SMALL)
+    esd, dsd = vae_state_dicts()
+    x, z, z2 = vae_inputs()
+    mean, logvar, att = gpt_vae_oracle.encoder_forward(esd, ecfg, x)
+    np.testing.assert_allclose(mean.numpy(), g["mean"], atol=2e-5)
+    np.testing.assert_allclose(logvar.numpy(), g["logvar"], atol=2e-5)
+    np.testing.assert_allclose(att[:, :, ::66].numpy(), g["att_enc_rows"], atol=1e-6)
+    # fully unmasked attention: the first row attends to every position
+    assert float(att[:, :, 0, -1].min()) > 0
+    np.testing.assert_allclose(gpt_vae_oracle.kl_to_standard_normal(mean, logvar).numpy(), g["kl"], rtol=1e-5)
+    np.testing.assert_allclose(gpt_vae_oracle.eval_inference_dist(mean, logvar, z2).numpy(), g["logq"], rtol=1e-5)
+    logits, _ = gpt_vae_oracle.decoder_forward(dsd, dcfg, x, z)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], atol=2e-5)
+    np.testing.assert_allclose(gpt_vae_oracle.reconstruct_error(dsd, dcfg, x, z).numpy(), g["rec"], rtol=1e-5)
+    total, rec, kl = gpt_vae_oracle.vae_loss(esd, ecfg, dsd, dcfg, x, z, 0.5)
+    np.testing.assert_allclose(total.numpy(), g["rec"][:, 0] + 0.5 * g["kl"], rtol=1e-5)
+    # greedy generation from z (sharpened head), first 24 steps
+    sharp = dict(dsd)
+    sharp["head.weight"] = dsd["head.weight"] * 8.0
+    toks, _ = gpt_vae_oracle.decoder_sample(sharp, dcfg, torch.zeros(3, 0, dtype=torch.long), z, steps=24)
+    assert np.array_equal(toks.numpy(), g["tokens"][:, :24].astype(np.int64))
