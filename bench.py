@@ -66,6 +66,9 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+NCU_DRAM_OVER_ALGORITHMIC = 1579.7 / 1448.1   # measured DRAM bytes / algorithmic bytes of a decode position (profiles/)
+
+
 def decode_algorithmic_bytes(batch, steps, cfg):
     """per decode step the bf16 weights are streamed once (independent of the batch),
     each sequence reads its KV cache (n positions) and appends one position."""
@@ -239,7 +242,12 @@ def run_ours(a):
                         "return_attention=False (the (B,16,T,T) attention map the reference also returns is an optional 288 MB logging by-product)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "gpt decode loop (265 positions, each a CUDA-graph launch of the per-layer kernels)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     # ncu dram__bytes_read+write over the 195 kernels of one position at context 133
+                     # (profiles/r1_decode_dram_ctx133.csv): 1579.7 MB against 1448.1 MB algorithmic -> x1.091, applied to
+                     # the whole generation (the 32-sequence GEMM tiles read 14 % of the weight bytes a second time)
+                     "traffic": int(gen_bytes * NCU_DRAM_OVER_ALGORITHMIC),
+                     "traffic_source": "ncu sample of one decode position (context 133) scaled to the generation",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_generation": gen_bytes},
         "clocks": clocks,

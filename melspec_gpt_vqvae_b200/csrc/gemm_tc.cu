@@ -43,13 +43,57 @@ struct KParams {
   int transpose_out;   // swap-AB: weights are the A operand, output written transposed
 };
 
+// ---- per-warp 32 x 64-byte transposer (2 KB of shared memory per warp)
+// The accumulator layout gives every lane one output ROW, so a direct store instruction touches 32 rows x 16 bytes:
+// 32 half-filled sectors per instruction.  Measured on the 80x848 convolutions: with the epilogue's global stores
+// and residual loads removed the kernel ran 26 % faster, with its arithmetic removed as well only 2 % more -- the
+// memory instructions were the cost.  Staging through shared memory turns every instruction into 8 rows x 64
+// contiguous bytes (16 full sectors).  "own" = lane l holds the 64 bytes of row l; "spread" = instruction i of lane l
+// holds 16-byte piece (l & 3) of row 8*i + (l >> 2).  The XOR keeps both access patterns bank-conflict free.
+constexpr int EPI_STAGE_BYTES = 32 * 64;
+__device__ __forceinline__ uint8_t* stage_own(uint8_t* buf, int lane, int j) {
+  return buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ uint8_t* stage_spread(uint8_t* buf, int lane, int i) {
+  const int r = 8 * i + (lane >> 2), c = lane & 3;
+  return buf + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void own_to_spread(uint8_t* buf, int lane, const uint4 (&in)[4], uint4 (&out)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stage_own(buf, lane, j)) = in[j];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = *reinterpret_cast<const uint4*>(stage_spread(buf, lane, i));
+  __syncwarp();
+}
+__device__ __forceinline__ void spread_to_own(uint8_t* buf, int lane, const uint4 (&in)[4], uint4 (&out)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage_spread(buf, lane, i)) = in[i];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[j] = *reinterpret_cast<const uint4*>(stage_own(buf, lane, j));
+  __syncwarp();
+}
+
 // Row-major epilogue of one accumulator tile: this thread owns accumulator row (TMEM lane) `quarter*32+lane`
 // and walks the BN columns in chunks of 32 (bias / GELU / residual / bf16 or fp32 store / split-K reduction /
-// GroupNorm partial sums into this warp's shared-memory bins).
+// GroupNorm partial sums into this warp's shared-memory bins).  `stage` = this warp's EPI_STAGE_BYTES transposer
+// buffer (nullptr: direct, uncoalesced path).
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const KParams& p, uint32_t tmem_base, int quarter, int lane, bool row_ok,
                                               long long out_row, int n0, bool add_bias, float* s_bins,
-                                              int c_begin = 0, int c_end = BN / 32) {
+                                              int c_begin = 0, int c_end = BN / 32, uint8_t* stage = nullptr) {
+    // element offsets / validity of the 4 rows this lane touches in the spread pattern
+    long long srow[4];
+    bool sok[4];
+    if (stage != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int src = 8 * i + (lane >> 2);
+        srow[i] = __shfl_sync(0xffffffffu, out_row, src);
+        sok[i] = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, src) != 0;
+      }
+    }
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       const int col0 = n0 + c * 32;
@@ -76,7 +120,26 @@ __device__ __forceinline__ void epilogue_rows(const KParams& p, uint32_t tmem_ba
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
-        if (p.epi == EPI_BF16_RESID && row_ok) {
+        if (p.epi == EPI_BF16_RESID && stage != nullptr) {
+          uint4 sp[4], own[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            sp[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (sok[i])
+              sp[i] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + srow[i] + col0) + (lane & 3));
+          }
+          spread_to_own(stage, lane, sp, own);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w[4] = {own[j].x, own[j].y, own[j].z, own[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(w[e]);
+              v[8 * j + 2 * e] += f.x;
+              v[8 * j + 2 * e + 1] += f.y;
+            }
+          }
+        } else if (p.epi == EPI_BF16_RESID && row_ok) {
           const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.resid) + out_row + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -93,7 +156,15 @@ __device__ __forceinline__ void epilogue_rows(const KParams& p, uint32_t tmem_ba
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-        if (row_ok) {
+        if (stage != nullptr) {
+          uint4 own[4], sp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) own[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          own_to_spread(stage, lane, own, sp);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (sok[i]) *(reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + srow[i] + col0) + (lane & 3)) = sp[i];
+        } else if (row_ok) {
           uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_row + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -158,6 +229,36 @@ __device__ __forceinline__ void epilogue_rows(const KParams& p, uint32_t tmem_ba
           const int nvals = 2 * (32 / gch);
           // each warp owns its bins (one writer per bin): plain, deterministic accumulation
           if ((lane & 1) == 0 && vidx < nvals) s_bins[quarter * 64 + c * nvals + vidx] += st[0];
+        }
+      } else if (stage != nullptr && p.epi != EPI_F32_ATOMIC) {
+        // fp32 rows are 128 bytes per chunk: two passes of 16 columns (64 bytes) through the transposer
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 own[4], sp[4];
+          if (p.epi == EPI_F32_RESID) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              sp[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (sok[i])
+                sp[i] = *(reinterpret_cast<const uint4*>(static_cast<const float*>(p.resid) + srow[i] + col0 + 16 * h) + (lane & 3));
+            }
+            spread_to_own(stage, lane, sp, own);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[16 * h + 4 * j + 0] += __uint_as_float(own[j].x);
+              v[16 * h + 4 * j + 1] += __uint_as_float(own[j].y);
+              v[16 * h + 4 * j + 2] += __uint_as_float(own[j].z);
+              v[16 * h + 4 * j + 3] += __uint_as_float(own[j].w);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            own[j] = make_uint4(__float_as_uint(v[16 * h + 4 * j]), __float_as_uint(v[16 * h + 4 * j + 1]),
+                                __float_as_uint(v[16 * h + 4 * j + 2]), __float_as_uint(v[16 * h + 4 * j + 3]));
+          own_to_spread(stage, lane, own, sp);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (sok[i]) *(reinterpret_cast<uint4*>(static_cast<float*>(p.out) + srow[i] + col0 + 16 * h) + (lane & 3)) = sp[i];
         }
       } else if (row_ok) {
         float* o = static_cast<float*>(p.out) + out_row + col0;
@@ -438,26 +539,41 @@ __device__ __forceinline__ PTile decode_tile(const KParams& p, int tile, int n_t
 }
 
 constexpr int PERSIST_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int KSUB = 2;                // k-blocks per pipeline stage (one barrier hand-off per KSUB k-blocks)
 
-template <int BN>
+// Measured on the 80x848 128->128 convolutions: with the loads, the MMAs and the epilogue all removed the
+// one-k-block-per-stage version of this kernel still took 56 % of its time -- the single MMA-issuing thread needs
+// ~500 cycles per k-block for its barrier wait, descriptor arithmetic (runtime modulo / division by the stage
+// count), four issues and the commit, while the tensor core finishes the four 128x128x16 MMAs in 256.  Hence: two
+// k-blocks per stage (half the hand-offs), stage / phase / tap counters instead of divisions, descriptors advanced
+// by adding to a precomputed base.
+// MT = M tiles per CTA.  MT = 2 (BN <= 128): the CTA owns two 128-row tiles that share every B tile, i.e. a 256 x BN
+// output block -- (256 + BN) operand rows per k-block instead of 2 x (128 + BN).  Once the issue loop was fixed the
+// 128 x 128 convolutions became bound by the L2 -> SM operand feed (~53 B/cycle/SM), so fewer bytes per FLOP is time.
+template <int BN, int MT>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const KParams p, int m_tiles, int n_tiles) {
+  static_assert(MT == 1 || (MT == 2 && BN <= 128), "two M tiles need 4 x BN <= 512 TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int B_STAGE_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int KB_BYTES = MT * A_STAGE_BYTES + B_STAGE_BYTES;     // one k-block: MT A tiles, then the B tile
+  constexpr int STAGE_BYTES = KSUB * KB_BYTES;
+  constexpr int ACC_COLS = MT * BN;                                // TMEM columns of one accumulator buffer
   const int stages = p.stages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_bins = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][64]
+  float* s_bins = reinterpret_cast<float*>(tmem_slot + 4);   // [MT][4 quarters][64] GroupNorm partial sums
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bins + MT * 256);   // [8 epilogue warps][EPI_STAGE_BYTES], 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = m_tiles * n_tiles;
+  const int m_groups = (m_tiles + MT - 1) / MT;
+  const int total_tiles = m_groups * n_tiles;        // CTA-level tiles (MT x 128 rows each)
   const int nkb = p.K / BK;
 
   if (threadIdx.x == 0) {
@@ -474,7 +590,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, 2 * ACC_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -482,29 +598,57 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // M tile `mt` (0..MT-1) of CTA-level tile `tile`; tiles past the end decode to out-of-range coordinates (TMA zero
+  // fill, stores masked by the caller)
+  auto sub_tile = [&](int tile, int mt) {
+    const int mg = tile / n_tiles;
+    const int nt = tile - mg * n_tiles;
+    return decode_tile(p, (mg * MT + mt) * n_tiles + nt, n_tiles, BN);
+  };
+
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       const int cblocks = (p.a_mode == A_PLAIN) ? 1 : (p.Cin / BK);
-      int it = 0;   // global k-block counter (ring position)
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const PTile t = decode_tile(p, tile, n_tiles, BN);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
+        PTile t[MT];
+        int xb[MT], yb[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          t[mt] = sub_tile(tile, mt);
+          xb[mt] = t[mt].x0 * p.stride - p.pad;
+          yb[mt] = t[mt].y0 * p.stride - p.pad;
+        }
+        int cb = 0, dx = 0, dy = 0;          // conv: channel block and filter tap of the next k-block
+        for (int kb = 0; kb < nkb; kb += KSUB) {
+          const int nsub = (nkb - kb < KSUB) ? nkb - kb : KSUB;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(nsub) * KB_BYTES);
           uint8_t* dst = smem + s * STAGE_BYTES;
-          if (p.a_mode == A_PLAIN) {
-            tma_load_2d(dst, &tmA, &full_bar[s], kb * BK, t.m0, kEvictNormal);
-          } else {
-            const int tap = kb / cblocks;
-            const int c0 = (kb - tap * cblocks) * BK;
-            const int dy = tap / 3, dx = tap - dy * 3;
-            tma_load_4d(dst, &tmA, &full_bar[s], c0, t.x0 * p.stride + dx - p.pad, t.y0 * p.stride + dy - p.pad, t.img,
-                        kEvictNormal);
+          for (int j = 0; j < nsub; ++j, dst += KB_BYTES) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              if (p.a_mode == A_PLAIN)
+                tma_load_2d(dst + mt * A_STAGE_BYTES, &tmA, &full_bar[s], (kb + j) * BK, t[mt].m0, kEvictNormal);
+              else
+                tma_load_4d(dst + mt * A_STAGE_BYTES, &tmA, &full_bar[s], cb * BK, xb[mt] + dx, yb[mt] + dy, t[mt].img,
+                            kEvictNormal);
+            }
+            if (p.a_mode != A_PLAIN && ++cb == cblocks) {
+              cb = 0;
+              if (++dx == 3) {
+                dx = 0;
+                ++dy;
+              }
+            }
+            tma_load_2d(dst + MT * A_STAGE_BYTES, &tmB, &full_bar[s], (kb + j) * BK, t[0].n0, kEvictLast);
           }
-          tma_load_2d(dst + A_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, t.n0, kEvictLast);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
     }
@@ -512,60 +656,80 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
-      int it = 0, lt = 0;
+      const uint64_t desc_a0 = make_smem_desc_sw128(smem_u32(smem));
+      const uint64_t desc_b0 = make_smem_desc_sw128(smem_u32(smem) + MT * A_STAGE_BYTES);
+      int s = 0, lt = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
         mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + as * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
+        const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
+        uint32_t acc = 0;
+        for (int kb = 0; kb < nkb; kb += KSUB) {
+          const int nsub = (nkb - kb < KSUB) ? nkb - kb : KSUB;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          // descriptor start-address field counts 16-byte units
+          uint64_t da = desc_a0 + static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
+          uint64_t db = desc_b0 + static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
+          for (int j = 0; j < nsub; ++j, da += KB_BYTES >> 4, db += KB_BYTES >> 4) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_acc, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {   // 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt)
+                umma_bf16(tmem_acc + mt * BN, da + mt * (A_STAGE_BYTES >> 4) + 2 * k, db + 2 * k, idesc, acc);
+              acc = 1;
+            }
+          }
           tc_commit(&empty_bar[s]);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
         }
         tc_commit(&tmem_full_bar[as]);
       }
     }
   } else {
     // =========================== epilogue ===========================
-    // warps 2..9: TMEM lane quarter = warp & 3 (hardware rule); the two warps of a quarter split the columns
+    // warps 2..9: TMEM lane quarter = warp & 3 (hardware rule).  MT = 1: the two warps of a quarter split the
+    // columns; MT = 2: each takes one of the two M tiles (all columns).
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int NCH = BN / 32;
-    const int c_begin = (NCH >= 2) ? half * (NCH / 2) : 0;
-    const int c_end = (NCH >= 2) ? c_begin + NCH / 2 : (half == 0 ? 1 : 0);
+    const int mt_mine = (MT == 2) ? half : 0;
+    const int c_begin = (MT == 2) ? 0 : ((NCH >= 2) ? half * (NCH / 2) : 0);
+    const int c_end = (MT == 2) ? NCH : ((NCH >= 2) ? c_begin + NCH / 2 : (half == 0 ? 1 : 0));
     const int r_local = quarter * 32 + lane;
     const int et = threadIdx.x - 64;      // epilogue thread index 0..255
+    float* my_bins = s_bins + mt_mine * 256;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const PTile t = decode_tile(p, tile, n_tiles, BN);
+      const PTile t = sub_tile(tile, mt_mine);
+      const bool tile_ok = (tile / n_tiles) * MT + mt_mine < m_tiles;
       const int as = lt & 1;
       bool row_ok;
       long long out_row;
       if (p.a_mode == A_PLAIN) {
         const int row = t.m0 + r_local;
-        row_ok = row < p.M;
+        row_ok = tile_ok && row < p.M;
         out_row = static_cast<long long>(row) * p.ldo;
       } else {
         const int ly = r_local / p.wb, lx = r_local - ly * p.wb;
         const int x = t.x0 + lx, y = t.y0 + ly;
-        row_ok = (x < p.W) && (y < p.H);
+        row_ok = tile_ok && (x < p.W) && (y < p.H);
         out_row = ((static_cast<long long>(t.img) * p.H + y) * p.W + x) * p.ldo;
       }
-      if (p.gn_sum != nullptr) s_bins[et] = 0.f;   // 256 bins = [4 quarters][64]; cleared after the previous flush barrier
-      if (p.gn_sum != nullptr) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (p.gn_sum != nullptr) {   // [MT][4 quarters][64] bins; cleared after the previous flush barrier
+        s_bins[et] = 0.f;
+        if (MT == 2) s_bins[256 + et] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
       tc_fence_after();
-      epilogue_rows<BN>(p, tmem_base + as * BN, quarter, lane, row_ok, out_row, t.n0, p.bias != nullptr, s_bins, c_begin,
-                        c_end);
+      epilogue_rows<BN>(p, tmem_base + as * ACC_COLS + mt_mine * BN, quarter, lane, row_ok, out_row, t.n0, p.bias != nullptr,
+                        my_bins, c_begin, c_end, s_stage + (warp - 2) * EPI_STAGE_BYTES);
       // accumulator fully read into registers: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[as]);
@@ -573,10 +737,18 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int nbins = (BN / p.gn_group_ch) * 2;
         const int groups_total = p.N / p.gn_group_ch;
-        const int g0 = t.n0 / p.gn_group_ch;
-        if (et < nbins && g0 + (et >> 1) < groups_total)
-          p.gn_sum[(t.stats_slot * groups_total + g0 + (et >> 1)) * 2 + (et & 1)] =
-              (s_bins[et] + s_bins[64 + et]) + (s_bins[128 + et] + s_bins[192 + et]);
+        // thread et < 128 flushes M tile 0, 128 <= et < 256 flushes M tile 1 (MT = 2)
+        const int fm = (MT == 2) ? (et >> 7) : 0;
+        const int eb = (MT == 2) ? (et & 127) : et;
+        if (fm < MT && eb < nbins) {
+          const PTile ft = sub_tile(tile, fm);
+          const int g0 = ft.n0 / p.gn_group_ch;
+          const bool f_ok = (tile / n_tiles) * MT + fm < m_tiles;
+          const float* bsrc = s_bins + fm * 256;
+          if (f_ok && g0 + (eb >> 1) < groups_total)
+            p.gn_sum[(ft.stats_slot * groups_total + g0 + (eb >> 1)) * 2 + (eb & 1)] =
+                (bsrc[eb] + bsrc[64 + eb]) + (bsrc[128 + eb] + bsrc[192 + eb]);
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");   // bins may be cleared for the next tile
       }
     }
@@ -586,7 +758,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, 2 * ACC_COLS);
   }
 }
 
@@ -718,14 +890,15 @@ int launch_tc(const GemmArgs& a, KParams& p) {
 }
 
 
-template <int BN>
+template <int BN, int MT>
 int launch_persist(const GemmArgs& a, KParams& p) {
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  constexpr int STAGE_BYTES = KSUB * (MT * A_STAGE_BYTES + BN * BK * 2);
   p.kb_per_split = a.K / BK;
-  int stages = (196 * 1024) / STAGE_BYTES;   // one CTA per SM: use the whole shared memory as the ring
-  if (stages > 8) stages = 8;
+  int stages = (200 * 1024) / STAGE_BYTES;   // one CTA per SM: the ring takes what the epilogue staging leaves
+  if (stages > 6) stages = 6;
+  if (stages < 1) stages = 1;
   p.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * STAGE_BYTES + (2 * stages + 4) * 8 + 16 + 1024 + 1024;
+  const size_t smem = static_cast<size_t>(stages) * STAGE_BYTES + (2 * stages + 4) * 8 + 16 + MT * 1024 + 8 * EPI_STAGE_BYTES + 1024;
   CUtensorMap tmA, tmB;
   int m_tiles;
   if (a.a_mode == A_PLAIN) {
@@ -740,15 +913,15 @@ int launch_persist(const GemmArgs& a, KParams& p) {
   const int n_tiles = ceil_div(a.N, BN);
   static bool attr_set = false;
   if (!attr_set) {
-    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, MT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  const int total = m_tiles * n_tiles;
+  const int total = ceil_div(m_tiles, MT) * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   LaunchCfg lc(dim3(grid), dim3(PERSIST_THREADS), smem, a.stream, false);
-  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_tc_persist_kernel<BN>, tmA, tmB, p, m_tiles, n_tiles));
+  MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_tc_persist_kernel<BN, MT>, tmA, tmB, p, m_tiles, n_tiles));
   return MGV_OK;
 }
 
@@ -763,12 +936,15 @@ int gemm_bf16_tc(const GemmArgs& a) {
   if (!a.transpose_out && a.split_k == 1 && !no_persist) {
     const long long tiles = a.a_mode == A_PLAIN ? static_cast<long long>(ceil_div(a.M, BM)) * ceil_div(a.N, a.bn)
                                                 : static_cast<long long>(p.tiles_x) * p.tiles_y * a.n_img * ceil_div(a.N, a.bn);
+    static const bool no_mt2 = getenv("MGV_NO_MT2") != nullptr;
     if (tiles > 2LL * num_sms()) {
+      // two M tiles per CTA (256 x BN output block) whenever the tile count allows it
+      const bool mt2 = !no_mt2 && tiles > 4LL * num_sms();
       switch (a.bn) {
-        case 32: return launch_persist<32>(a, p);
-        case 64: return launch_persist<64>(a, p);
-        case 128: return launch_persist<128>(a, p);
-        case 256: return launch_persist<256>(a, p);
+        case 32: return launch_persist<32, 1>(a, p);
+        case 64: return mt2 ? launch_persist<64, 2>(a, p) : launch_persist<64, 1>(a, p);
+        case 128: return mt2 ? launch_persist<128, 2>(a, p) : launch_persist<128, 1>(a, p);
+        case 256: return launch_persist<256, 1>(a, p);
         default: break;
       }
     }

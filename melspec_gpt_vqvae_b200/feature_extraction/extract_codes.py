@@ -55,8 +55,10 @@ def _load_mel(mel_path, transforms):
 
 @torch.no_grad()
 def encode_batch(mels, device, model):
-    """(B,80,848) float32 numpy in [-1,1] -> (B,5,53) int64 numpy codes."""
-    x = torch.from_numpy(np.ascontiguousarray(mels)).unsqueeze(1).to(device, non_blocking=True)
+    """(B,80,848) float32 (numpy array or pinned host tensor) in [-1,1] -> (B,5,53) int64 numpy codes."""
+    if not torch.is_tensor(mels):
+        mels = torch.from_numpy(np.ascontiguousarray(mels))
+    x = mels.unsqueeze(1).to(device, non_blocking=True)
     y = model.encode(x)
     idx = model._vq_vae.encoding_indices(y)              # == info[2] of model._vq_vae(y)
     return idx.reshape(x.shape[0], y.shape[2], y.shape[3]).cpu().numpy()
@@ -78,31 +80,64 @@ def get_codes(mel_path, device, spec_crop_len, model, transforms, folder_name='c
         print("\rfile exists:", mel_path, end="", flush=True)
 
 
-def get_codes_batch(mel_paths, device, spec_crop_len, model, transforms, folder_name='codes_10s', batch_size=64):
-    """Batched walk: same per-file results as calling get_codes on each path."""
-    todo = [p for p in mel_paths if not os.path.isfile(_out_path(p, folder_name))]
-    done = 0
-    for i in range(0, len(todo), batch_size):
-        chunk, mels = [], []
-        for p in todo[i:i + batch_size]:
-            try:
-                mels.append(_load_mel(p, transforms))
-                chunk.append(p)
-            except Exception:
-                print(p, "is damaged")
-        if not chunk:
-            continue
+def _load_many(paths, transforms, pool):
+    """-> (good paths, float32 array (n,80,W) in [-1,1]); damaged files are reported and skipped like get_codes does"""
+    def one(p):
         try:
-            codes = encode_batch(np.stack(mels), device, model)
+            return p, _load_mel(p, transforms)
         except Exception:
-            for p in chunk:
-                print(p, "is damaged")
-            continue
-        for p, c in zip(chunk, codes):
-            out = _out_path(p, folder_name)
-            os.makedirs(os.path.dirname(out), exist_ok=True)
-            np.save(out, c)
-            done += 1
+            print(p, "is damaged")
+            return p, None
+    res = [r for r in pool.map(one, paths) if r[1] is not None]
+    if not res:
+        return [], None
+    return [r[0] for r in res], np.stack([r[1] for r in res])
+
+
+def _save_code(out, codes):
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    np.save(out, codes)
+
+
+def get_codes_batch(mel_paths, device, spec_crop_len, model, transforms, folder_name='codes_10s', batch_size=64,
+                    io_threads=8):
+    """Batched walk with the same per-file results as calling get_codes on each path.
+
+    Three overlapped stages so that the encoder (~3 000 clips/s on one B200) is not I/O-bound: a thread pool loads
+    and crops the next batch of `*_mel.npy` files while the GPU works on the current one, batches go through a
+    pinned host staging buffer with an asynchronous copy, and the (5,53) int64 code files are written by the pool."""
+    from concurrent.futures import ThreadPoolExecutor
+    todo = [p for p in mel_paths if not os.path.isfile(_out_path(p, folder_name))]
+    if not todo:
+        return 0
+    chunks = [todo[i:i + batch_size] for i in range(0, len(todo), batch_size)]
+    done = 0
+    writes = []
+    staging = [None, None]                       # two pinned buffers: batch i+1 is staged while batch i is in flight
+    with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool, ThreadPoolExecutor(max_workers=1) as prefetch:
+        nxt = prefetch.submit(_load_many, chunks[0], transforms, pool)
+        for i in range(len(chunks)):
+            chunk, mels = nxt.result()
+            if i + 1 < len(chunks):
+                nxt = prefetch.submit(_load_many, chunks[i + 1], transforms, pool)
+            if not chunk:
+                continue
+            try:
+                buf = staging[i & 1]
+                if buf is None or buf.shape[0] < mels.shape[0] or buf.shape[1:] != mels.shape[1:]:
+                    buf = staging[i & 1] = torch.empty((max(batch_size, mels.shape[0]),) + mels.shape[1:],
+                                                       dtype=torch.float32).pin_memory()
+                buf[:mels.shape[0]].copy_(torch.from_numpy(mels))
+                codes = encode_batch(buf[:mels.shape[0]], device, model)
+            except Exception:
+                for p in chunk:
+                    print(p, "is damaged")
+                continue
+            for p, c in zip(chunk, codes):
+                writes.append(pool.submit(_save_code, _out_path(p, folder_name), c))
+                done += 1
+        for w in writes:
+            w.result()
     return done
 
 
