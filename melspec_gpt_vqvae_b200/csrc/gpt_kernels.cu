@@ -100,15 +100,18 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 // ------------------------------------------------------------------ prefill attention
 // Causal (or prefix-unmasked) attention over a whole sequence, T <= 288, head dim 64, on the legacy tensor path
 // (mma.sync m16n8k16 bf16 -> fp32; this part is 4% of the prefill FLOPs, the GEMMs around it are tcgen05).
-// CTA = 4 warps = 64 query rows of one (sequence, head); K and V rows of the head are staged once in shared
-// memory (rows padded to 144 B: conflict-free fragment loads and ldmatrix).  Two passes over the key blocks:
-// pass 1 computes the exact row maximum and sum, pass 2 recomputes the scores, emits the normalised
-// probabilities (last layer only, fp32) and accumulates P V.  No [T,T] tensor ever reaches HBM except when the
-// caller asks for the attention map.
-constexpr int FA_BM = 64;
-constexpr int FA_BN = 64;
+// One CTA = one (sequence, head): K and V of the head are staged ONCE in shared memory (rows padded to 144 B:
+// conflict-free fragment loads and ldmatrix) and 9 warps walk the 16-row query blocks in causal-balanced pairs
+// (block w and block n-1-w see the same number of keys in total).  Flash-style single pass with an online softmax
+// (running max / sum per row, accumulator rescaled per 64-key block) -- except when the caller wants the attention
+// map (the last layer): then pass 1 finds the exact row maximum and sum and pass 2 emits the normalised
+// probabilities (fp32) while it accumulates P V.  No [T,T] tensor reaches HBM otherwise.
+// (First version: one CTA per 64 query rows, K/V restaged per CTA, always two passes: 370 us per layer at
+// bs=64 against 100 us for all four GEMMs of the layer.)
+constexpr int FA_BN = 64;          // keys per block
 constexpr int FA_LD = 72;          // bf16 elements per smem row (64 + 8 pad)
-constexpr int FA_THREADS = 128;
+constexpr int FA_WARPS = 9;        // ceil(288 / 16 / 2) query-block pairs
+constexpr int FA_THREADS = FA_WARPS * 32;
 constexpr int FA_MAXK = 320;       // >= GPT_MAX_T rounded up to FA_BN
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -123,41 +126,29 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
                : "r"(smem_u32(smem_row)));
 }
 
+template <bool WRITE_ATT>
 __global__ void __launch_bounds__(FA_THREADS)
 attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T, int nh, int n_unmasked,
                     __nv_bfloat16* __restrict__ y, float* __restrict__ att, int att_T,
                     __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache, int Tmax) {
   extern __shared__ __align__(16) __nv_bfloat16 fa_smem[];
-  __nv_bfloat16* sQ = fa_smem;                       // [64][72]
-  __nv_bfloat16* sK = sQ + FA_BM * FA_LD;            // [kpad][72]
-  const int bh = blockIdx.y;
+  const int kpad = ((T + FA_BN - 1) / FA_BN) * FA_BN;
+  __nv_bfloat16* sK = fa_smem;                       // [kpad][72]
+  __nv_bfloat16* sV = sK + kpad * FA_LD;             // [kpad][72]
+  const int bh = blockIdx.x;
   const int b = bh / nh, h = bh - b * nh;
   const int C = nh * GPT_HEAD_DIM;
-  const int q0 = blockIdx.x * FA_BM;
-  const int q_end = min(q0 + FA_BM, T);
-  const int kmax = (q0 < n_unmasked) ? max(q_end, min(n_unmasked, T)) : q_end;   // keys any row of this block may see
-  const int nkb = (kmax + FA_BN - 1) / FA_BN;
-  const int kpad = nkb * FA_BN;
-  __nv_bfloat16* sV = sK + kpad * FA_LD;             // [kpad][72]
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
-  // ---- stage Q (this block's rows), K and V (rows < kmax; zero beyond) ; the last block also fills the KV cache
-  const bool write_cache = (kcache != nullptr) && (blockIdx.x == gridDim.x - 1);   // last block sees every key
-  for (int i = t; i < FA_BM * 8; i += FA_THREADS) {
-    const int r = i >> 3, part = i & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q0 + r < T)
-      v = *reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(b) * T + q0 + r) * (3 * C) + h * GPT_HEAD_DIM + part * 8);
-    *reinterpret_cast<uint4*>(sQ + r * FA_LD + part * 8) = v;
-  }
+  // ---- stage K and V (zero beyond T); also fills the KV cache
   for (int i = t; i < kpad * 8; i += FA_THREADS) {
     const int r = i >> 3, part = i & 7;
     uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
-    if (r < kmax) {
+    if (r < T) {
       const __nv_bfloat16* base = qkv + (static_cast<long long>(b) * T + r) * (3 * C) + h * GPT_HEAD_DIM + part * 8;
       kq = *reinterpret_cast<const uint4*>(base + C);
       vq = *reinterpret_cast<const uint4*>(base + 2 * C);
-      if (write_cache) {
+      if (kcache != nullptr) {
         const long long co = ((static_cast<long long>(b) * nh + h) * Tmax + r) * GPT_HEAD_DIM + part * 8;
         *reinterpret_cast<uint4*>(kcache + co) = kq;
         *reinterpret_cast<uint4*>(vcache + co) = vq;
@@ -168,132 +159,195 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T, int nh,
   }
   __syncthreads();
 
-  // ---- this warp's 16 query rows; thread owns rows (g, g+8) and column pairs 2*tq, 2*tq+1 of every 8-wide block
+  const int nrb = (T + 15) / 16;                       // 16-row query blocks
   const int g = lane >> 2, tq = lane & 3;
-  const int rbase = q0 + warp * 16;
-  if (rbase >= T) return;                              // warp-uniform: nothing to do for a fully padded warp
-  const int row0 = min(rbase + g, T - 1), row1 = min(rbase + g + 8, T - 1);   // padded rows mirror the last row
-  uint32_t aq[4][4];
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const __nv_bfloat16* qa = sQ + (warp * 16 + g) * FA_LD + kk * 16 + tq * 2;
-    aq[kk][0] = *reinterpret_cast<const uint32_t*>(qa);
-    aq[kk][1] = *reinterpret_cast<const uint32_t*>(qa + 8 * FA_LD);
-    aq[kk][2] = *reinterpret_cast<const uint32_t*>(qa + 8);
-    aq[kk][3] = *reinterpret_cast<const uint32_t*>(qa + 8 * FA_LD + 8);
-  }
-  const float scale = 1.0f / sqrtf(static_cast<float>(GPT_HEAD_DIM));   // minGPT.py:81
-  // keys this warp's rows can see: causal limit of its last row, or the unmasked prefix
-  const int wlast = min(rbase + 15, T - 1);
-  const int wkmax = (rbase < n_unmasked) ? max(wlast + 1, min(n_unmasked, T)) : wlast + 1;
-  const int wnkb = (wkmax + FA_BN - 1) / FA_BN;
+  // 1/sqrt(d) (minGPT.py:81) folded with log2(e): probabilities are exp2(s' - max')
+  const float scale2 = 1.4426950408889634f / sqrtf(static_cast<float>(GPT_HEAD_DIM));
 
-  auto scores = [&](int jb, float (&sc)[8][4]) {
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      sc[nb][0] = sc[nb][1] = sc[nb][2] = sc[nb][3] = 0.f;
-      const __nv_bfloat16* kb = sK + (jb * FA_BN + nb * 8 + g) * FA_LD + tq * 2;
+  for (int turn = 0; turn < 2; ++turn) {
+    // causal-balanced pairing: warp w takes block w, then block nrb-1-w
+    const int rb = (turn == 0) ? warp : nrb - 1 - warp;
+    if (turn == 0 ? (2 * warp >= nrb) : (rb <= warp)) continue;   // warp-uniform
+    const int rbase = rb * 16;
+    const int row0 = min(rbase + g, T - 1), row1 = min(rbase + g + 8, T - 1);   // padded rows mirror the last row
+    const bool r0_ok = rbase + g < T, r1_ok = rbase + g + 8 < T;
+    // Q fragments straight from global memory (each row block is read once)
+    uint32_t aq[4][4];
+    {
+      const __nv_bfloat16* q0p = qkv + (static_cast<long long>(b) * T + row0) * (3 * C) + h * GPT_HEAD_DIM + tq * 2;
+      const __nv_bfloat16* q1p = qkv + (static_cast<long long>(b) * T + row1) * (3 * C) + h * GPT_HEAD_DIM + tq * 2;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kb + kk * 16);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kb + kk * 16 + 8);
-        mma_bf16_16816(sc[nb], aq[kk], b0, b1);
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = jb * FA_BN + nb * 8 + tq * 2 + (e & 1);
-        const int row = (e < 2) ? row0 : row1;
-        // mask[i][j] = tril, plus the unmasked prefix block (minGPT.py:65-68, :82)
-        const bool allowed = key < T && (key <= row || (row < n_unmasked && key < n_unmasked));
-        sc[nb][e] = allowed ? sc[nb][e] * scale : -INFINITY;
+        aq[kk][0] = *reinterpret_cast<const uint32_t*>(q0p + kk * 16);
+        aq[kk][1] = *reinterpret_cast<const uint32_t*>(q1p + kk * 16);
+        aq[kk][2] = *reinterpret_cast<const uint32_t*>(q0p + kk * 16 + 8);
+        aq[kk][3] = *reinterpret_cast<const uint32_t*>(q1p + kk * 16 + 8);
       }
     }
-  };
+    // keys this block's rows can see: causal limit of its last row, or the unmasked prefix
+    const int wlast = min(rbase + 15, T - 1);
+    const int wkmax = (rbase < n_unmasked) ? max(wlast + 1, min(n_unmasked, T)) : wlast + 1;
+    const int wnkb = (wkmax + FA_BN - 1) / FA_BN;
 
-  // ---- pass 1: exact row max and sum
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  for (int jb = 0; jb < wnkb; ++jb) {
-    float sc[8][4];
-    scores(jb, sc);
-    float bm0 = -INFINITY, bm1 = -INFINITY;
+    auto scores = [&](int jb, float (&sc)[8][4]) {
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      bm0 = fmaxf(bm0, fmaxf(sc[nb][0], sc[nb][1]));
-      bm1 = fmaxf(bm1, fmaxf(sc[nb][2], sc[nb][3]));
-    }
-    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-    const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);   // key 0 is always allowed -> finite from block 0 on
-    float s0 = 0.f, s1 = 0.f;
+      for (int nb = 0; nb < 8; ++nb) {
+        sc[nb][0] = sc[nb][1] = sc[nb][2] = sc[nb][3] = 0.f;
+        const __nv_bfloat16* kb = sK + (jb * FA_BN + nb * 8 + g) * FA_LD + tq * 2;
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      s0 += expf(sc[nb][0] - n0) + expf(sc[nb][1] - n0);
-      s1 += expf(sc[nb][2] - n1) + expf(sc[nb][3] - n1);
-    }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    l0 = l0 * expf(m0 - n0) + s0;
-    l1 = l1 * expf(m1 - n1) + s1;
-    m0 = n0;
-    m1 = n1;
-  }
-  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kb + kk * 16);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kb + kk * 16 + 8);
+          mma_bf16_16816(sc[nb], aq[kk], b0, b1);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = jb * FA_BN + nb * 8 + tq * 2 + (e & 1);
+          const int row = (e < 2) ? row0 : row1;
+          // mask[i][j] = tril, plus the unmasked prefix block (minGPT.py:65-68, :82)
+          const bool allowed = key < T && (key <= row || (row < n_unmasked && key < n_unmasked));
+          sc[nb][e] = allowed ? sc[nb][e] * scale2 : -INFINITY;
+        }
+      }
+    };
+    auto block_max = [&](const float (&sc)[8][4], float& bm0, float& bm1) {
+      bm0 = -INFINITY;
+      bm1 = -INFINITY;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        bm0 = fmaxf(bm0, fmaxf(sc[nb][0], sc[nb][1]));
+        bm1 = fmaxf(bm1, fmaxf(sc[nb][2], sc[nb][3]));
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    };
+    auto pv = [&](int jb, const float (&sc)[8][4], float (&o)[8][4]) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {     // 16 keys per step
+        uint32_t ap[4];
+        ap[0] = pack_bf16x2(sc[2 * ks][0], sc[2 * ks][1]);
+        ap[1] = pack_bf16x2(sc[2 * ks][2], sc[2 * ks][3]);
+        ap[2] = pack_bf16x2(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
+        ap[3] = pack_bf16x2(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
+        const __nv_bfloat16* vrow = sV + (jb * FA_BN + ks * 16 + (lane & 15)) * FA_LD;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+          uint32_t b0, b1;
+          ldmatrix_x2_trans(b0, b1, vrow + nd * 8);
+          mma_bf16_16816(o[nd], ap, b0, b1);
+        }
+      }
+    };
 
-  // ---- pass 2: probabilities (+ optional attention map) and O = P V
-  float o[8][4];
+    float o[8][4];
 #pragma unroll
-  for (int nd = 0; nd < 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
-  const bool r0_ok = rbase + g < T, r1_ok = rbase + g + 8 < T;
-  float* arow0 = (att && r0_ok && row0 < att_T) ? att + ((static_cast<long long>(b) * nh + h) * att_T + row0) * att_T : nullptr;
-  float* arow1 = (att && r1_ok && row1 < att_T) ? att + ((static_cast<long long>(b) * nh + h) * att_T + row1) * att_T : nullptr;
-  for (int jb = 0; jb < wnkb; ++jb) {
-    float sc[8][4];
-    scores(jb, sc);
+    for (int nd = 0; nd < 8; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // l: this lane's share of the row sum
+    if (!WRITE_ATT) {
+      // ---- single pass, online softmax (key 0 is always allowed -> the maximum is finite from block 0 on)
+      for (int jb = 0; jb < wnkb; ++jb) {
+        float sc[8][4];
+        scores(jb, sc);
+        float bm0, bm1;
+        block_max(sc, bm0, bm1);
+        const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
+        const float a0 = exp2f(m0 - n0), a1 = exp2f(m1 - n1);
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      sc[nb][0] = expf(sc[nb][0] - m0) * inv0;
-      sc[nb][1] = expf(sc[nb][1] - m0) * inv0;
-      sc[nb][2] = expf(sc[nb][2] - m1) * inv1;
-      sc[nb][3] = expf(sc[nb][3] - m1) * inv1;
-      const int key = jb * FA_BN + nb * 8 + tq * 2;
-      if (arow0) {   // buffer is pre-zeroed: write only non-zero probabilities
-        if (key < att_T && sc[nb][0] != 0.f) arow0[key] = sc[nb][0];
-        if (key + 1 < att_T && sc[nb][1] != 0.f) arow0[key + 1] = sc[nb][1];
+        for (int nb = 0; nb < 8; ++nb) {
+          sc[nb][0] = exp2f(sc[nb][0] - n0);
+          sc[nb][1] = exp2f(sc[nb][1] - n0);
+          sc[nb][2] = exp2f(sc[nb][2] - n1);
+          sc[nb][3] = exp2f(sc[nb][3] - n1);
+          s0 += sc[nb][0] + sc[nb][1];
+          s1 += sc[nb][2] + sc[nb][3];
+        }
+        l0 = l0 * a0 + s0;
+        l1 = l1 * a1 + s1;
+        m0 = n0;
+        m1 = n1;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+          o[nd][0] *= a0;
+          o[nd][1] *= a0;
+          o[nd][2] *= a1;
+          o[nd][3] *= a1;
+        }
+        pv(jb, sc, o);
       }
-      if (arow1) {
-        if (key < att_T && sc[nb][2] != 0.f) arow1[key] = sc[nb][2];
-        if (key + 1 < att_T && sc[nb][3] != 0.f) arow1[key + 1] = sc[nb][3];
-      }
-    }
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {     // 16 keys per step
-      uint32_t ap[4];
-      ap[0] = pack_bf16x2(sc[2 * ks][0], sc[2 * ks][1]);
-      ap[1] = pack_bf16x2(sc[2 * ks][2], sc[2 * ks][3]);
-      ap[2] = pack_bf16x2(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
-      ap[3] = pack_bf16x2(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
-      const __nv_bfloat16* vrow = sV + (jb * FA_BN + ks * 16 + (lane & 15)) * FA_LD;
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
 #pragma unroll
       for (int nd = 0; nd < 8; ++nd) {
-        uint32_t b0, b1;
-        ldmatrix_x2_trans(b0, b1, vrow + nd * 8);
-        mma_bf16_16816(o[nd], ap, b0, b1);
+        o[nd][0] *= inv0;
+        o[nd][1] *= inv0;
+        o[nd][2] *= inv1;
+        o[nd][3] *= inv1;
+      }
+    } else {
+      // ---- pass 1: exact row maximum and sum
+      for (int jb = 0; jb < wnkb; ++jb) {
+        float sc[8][4];
+        scores(jb, sc);
+        float bm0, bm1;
+        block_max(sc, bm0, bm1);
+        const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          s0 += exp2f(sc[nb][0] - n0) + exp2f(sc[nb][1] - n0);
+          s1 += exp2f(sc[nb][2] - n1) + exp2f(sc[nb][3] - n1);
+        }
+        l0 = l0 * exp2f(m0 - n0) + s0;
+        l1 = l1 * exp2f(m1 - n1) + s1;
+        m0 = n0;
+        m1 = n1;
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+      // ---- pass 2: normalised probabilities -> attention map, and O = P V
+      float* arow0 = (att && r0_ok && row0 < att_T) ? att + ((static_cast<long long>(b) * nh + h) * att_T + row0) * att_T : nullptr;
+      float* arow1 = (att && r1_ok && row1 < att_T) ? att + ((static_cast<long long>(b) * nh + h) * att_T + row1) * att_T : nullptr;
+      for (int jb = 0; jb < wnkb; ++jb) {
+        float sc[8][4];
+        scores(jb, sc);
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          sc[nb][0] = exp2f(sc[nb][0] - m0) * inv0;
+          sc[nb][1] = exp2f(sc[nb][1] - m0) * inv0;
+          sc[nb][2] = exp2f(sc[nb][2] - m1) * inv1;
+          sc[nb][3] = exp2f(sc[nb][3] - m1) * inv1;
+          const int key = jb * FA_BN + nb * 8 + tq * 2;
+          if (arow0) {   // buffer is pre-zeroed: write only non-zero probabilities
+            if (key < att_T && sc[nb][0] != 0.f) arow0[key] = sc[nb][0];
+            if (key + 1 < att_T && sc[nb][1] != 0.f) arow0[key + 1] = sc[nb][1];
+          }
+          if (arow1) {
+            if (key < att_T && sc[nb][2] != 0.f) arow1[key] = sc[nb][2];
+            if (key + 1 < att_T && sc[nb][3] != 0.f) arow1[key + 1] = sc[nb][3];
+          }
+        }
+        pv(jb, sc, o);
       }
     }
-  }
 #pragma unroll
-  for (int nd = 0; nd < 8; ++nd) {
-    const int dim = nd * 8 + tq * 2;
-    if (r0_ok)
-      *reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b) * T + rbase + g) * C + h * GPT_HEAD_DIM + dim) =
-          pack_bf16x2(o[nd][0], o[nd][1]);
-    if (r1_ok)
-      *reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b) * T + rbase + g + 8) * C + h * GPT_HEAD_DIM + dim) =
-          pack_bf16x2(o[nd][2], o[nd][3]);
+    for (int nd = 0; nd < 8; ++nd) {
+      const int dim = nd * 8 + tq * 2;
+      if (r0_ok)
+        *reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b) * T + rbase + g) * C + h * GPT_HEAD_DIM + dim) =
+            pack_bf16x2(o[nd][0], o[nd][1]);
+      if (r1_ok)
+        *reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b) * T + rbase + g + 8) * C + h * GPT_HEAD_DIM + dim) =
+            pack_bf16x2(o[nd][2], o[nd][3]);
+    }
   }
 }
 
@@ -733,20 +787,26 @@ int gpt_layernorm(const float* x, const float* w, const float* b, int rows, int 
 
 int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_unmasked, __nv_bfloat16* y, float* att,
                           int att_T, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int Tmax, cudaStream_t s) {
-  MGV_REQUIRE(T >= 1 && T <= GPT_MAX_T, "attention: T=%d exceeds %d", T, GPT_MAX_T);
+  MGV_REQUIRE(T >= 1 && T <= GPT_MAX_T && (T + 15) / 16 <= 2 * FA_WARPS, "attention: T=%d exceeds %d", T, GPT_MAX_T);
   if (B == 0) return MGV_OK;
   const int kpad = ceil_div(T, FA_BN) * FA_BN;
-  const size_t smem = static_cast<size_t>(FA_BM + 2 * kpad) * FA_LD * sizeof(__nv_bfloat16);
+  const size_t smem = static_cast<size_t>(2 * kpad) * FA_LD * sizeof(__nv_bfloat16);
   static bool attr_set = false;
   if (!attr_set) {
-    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (FA_BM + 2 * FA_MAXK) * FA_LD * 2));
-    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2 * FA_MAXK * FA_LD * 2));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2 * FA_MAXK * FA_LD * 2));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  dim3 grid(ceil_div(T, FA_BM), B * nh);
-  attn_prefill_kernel<<<grid, FA_THREADS, smem, s>>>(qkv, B, T, nh, n_unmasked, y, att, att_T, kcache, vcache, Tmax);
+  if (att != nullptr)
+    attn_prefill_kernel<true><<<B * nh, FA_THREADS, smem, s>>>(qkv, B, T, nh, n_unmasked, y, att, att_T, kcache, vcache, Tmax);
+  else
+    attn_prefill_kernel<false><<<B * nh, FA_THREADS, smem, s>>>(qkv, B, T, nh, n_unmasked, y, att, att_T, kcache, vcache, Tmax);
   MGV_CHECK_CUDA(cudaGetLastError());
   return MGV_OK;
 }
