@@ -360,10 +360,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint64_t hint_b = swap_ab ? kEvictNormal : hint_w;
       const uint64_t hint_a = swap_ab ? hint_w : kEvictNormal;
       const int cblocks = (DECODE || p.a_mode == A_PLAIN) ? 1 : (p.Cin / BK);
-      auto load_a = [&](int kb, int s) {
+      auto load_a = [&](int kb, int s, uint64_t* bar = nullptr) {
         uint8_t* dst = smem + s * STAGE_BYTES;
+        if (bar == nullptr) bar = &full_bar[s];
         if (DECODE || p.a_mode == A_PLAIN) {
-          tma_load_2d(dst, &tmA, &full_bar[s], (kb0 + kb) * BK, m0, hint_a);
+          tma_load_2d(dst, &tmA, bar, (kb0 + kb) * BK, m0, hint_a);
         } else {
           const int kk = kb0 + kb;
           const int tap = kk / cblocks;
@@ -372,13 +373,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // input coordinate of the tile's first pixel for this tap
           const int xi = x0 * p.stride + dx - p.pad;
           const int yi = y0 * p.stride + dy - p.pad;
-          tma_load_4d(dst, &tmA, &full_bar[s], c0, xi, yi, img, hint_a);
+          tma_load_4d(dst, &tmA, bar, c0, xi, yi, img, hint_a);
         }
       };
-      auto load_b = [&](int kb, int s) {
+      auto load_b = [&](int kb, int s, uint64_t* bar = nullptr) {
         uint8_t* dst = smem + s * STAGE_BYTES + A_STAGE_BYTES;
-        tma_load_2d(dst, &tmB, &full_bar[s], (kb0 + kb) * BK, n0, hint_b);
+        if (bar == nullptr) bar = &full_bar[s];
+        tma_load_2d(dst, &tmB, bar, (kb0 + kb) * BK, n0, hint_b);
       };
+      if (DECODE && nkb <= stages) {
+        // Decode fast path: the whole K slice is resident, so there is no ring to manage -- one barrier for the weight
+        // tiles (issued before the grid dependency resolves), one for the activation tiles, one MMA burst, one commit.
+        // (Per k-block hand-offs cost the issuing threads ~0.25 us each: see gemm_tc_persist_kernel.)
+        uint64_t* w_bar = &full_bar[0];
+        uint64_t* x_bar = &empty_bar[0];
+        mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(nkb) * A_STAGE_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) load_a(kb, kb, w_bar);
+        pdl_wait();
+        mbar_arrive_expect_tx(x_bar, static_cast<uint32_t>(nkb) * B_STAGE_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) load_b(kb, kb, x_bar);
+      } else {
       const int pre = nkb < stages ? nkb : stages;
       for (int kb = 0; kb < pre; ++kb) {  // weights first: they do not depend on the upstream grid
         mbar_arrive_expect_tx(&full_bar[kb], STAGE_BYTES);
@@ -396,11 +410,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         load_a(kb, s);
         load_b(kb, s);
       }
+      }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+      if (DECODE && nkb <= stages) {
+        mbar_wait(&full_bar[0], 0);    // weights
+        mbar_wait(&empty_bar[0], 0);   // activations
+        tc_fence_after();
+        const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem));
+        const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem) + A_STAGE_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint64_t off = static_cast<uint64_t>((kb * STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da0 + off + 2 * k, db0 + off + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+      } else
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % stages;
         const uint32_t ph = (kb / stages) & 1;
