@@ -45,7 +45,7 @@ struct GptLayer {
 
 // split-K factors of the decode-step GEMMs (swap-AB: 128 weight rows per CTA x split-K slices)
 struct DecodeTiles {
-  int qkv_split = 8;    // 24 row tiles x 8  = 192 CTAs
+  int qkv_split = 4;    // 24 row tiles x 4 (x 2 sequence halves at batch 64) = 192 CTAs
   int proj_split = 16;  //  8 row tiles x 16 = 128 CTAs
   int fc1_split = 4;    // 32 row tiles x 4  = 128 CTAs
   int fc2_split = 16;   //  8 row tiles x 16 = 128 CTAs

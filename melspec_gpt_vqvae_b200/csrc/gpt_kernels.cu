@@ -69,6 +69,19 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
       s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     }
   }
+  // parameters: issue the loads now so that they are in flight during the two reductions (decode: C = 1024 -> 8 + 8
+  // float4 per lane; the latency of a dependent load is a measurable part of a 3 us stage)
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(bia);
+  float4 gq[LN_MAX_V4 / 2], bq[LN_MAX_V4 / 2];
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V4 / 2; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      gq[j] = __ldg(w4 + i);
+      bq[j] = __ldg(b4 + i);
+    }
+  }
   const float mean = warp_sum(s) / static_cast<float>(C);
   float ss = 0.f;
 #pragma unroll
@@ -80,14 +93,12 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     }
   }
   const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(C) + 1e-5f);
-  const float4* w4 = reinterpret_cast<const float4*>(w);
-  const float4* b4 = reinterpret_cast<const float4*>(bia);
   uint2* o2 = reinterpret_cast<uint2*>(out + static_cast<long long>(row) * C);
 #pragma unroll
   for (int j = 0; j < LN_MAX_V4; ++j) {
     const int i = lane + 32 * j;
     if (i < nv) {
-      const float4 g = __ldg(w4 + i), be = __ldg(b4 + i);
+      const float4 g = (j < LN_MAX_V4 / 2) ? gq[j] : __ldg(w4 + i), be = (j < LN_MAX_V4 / 2) ? bq[j] : __ldg(b4 + i);
       const float a = (v[j].x - mean) * rstd * g.x + be.x;
       const float b = (v[j].y - mean) * rstd * g.y + be.y;
       const float c = (v[j].z - mean) * rstd * g.z + be.z;
