@@ -71,6 +71,11 @@ int gemm_decode_gelu(const void* W, int Nw, int K, const float* src_f32, int B, 
 int gemm_decode_ln(const void* W, int Nw, int K, const float* x_f32, int B, const float* gamma, const float* beta,
                    const float* bias, float* out, long long ldo, int split_k, bool pdl, cudaStream_t stream);
 
+// Decode-step GEMM without split-K (gemm_decode_fullk.cu): a CTA = 128 weight rows x 32 sequences x all of K;
+// epi in {EPI_BF16_GELU, EPI_F32, EPI_F32_RESID}; W bf16 [Nw, K], X bf16 [B, K], K % 256 == 0.
+int gemm_decode_fullk(const void* W, int Nw, int K, const void* X_bf16, int B, const float* bias, int epi, void* out,
+                      const void* resid, long long ldo, bool pdl, cudaStream_t stream);
+
 // SIMT fp32 reference of the same contract (tests / on-device cross-checks only).
 int gemm_bf16_ref(const GemmArgs& a);
 

@@ -523,7 +523,12 @@ int enqueue_group_step(Gpt* g, int b0, int B, const SampleArgs& sa, float* att_o
                                  (l == g->L - 1) ? att_out : nullptr, att_T, qs, nullptr, 0, s, g->pdl));
     MGV_TRY(decode_gemm(g, dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, dx, dx, s));
     MGV_TRY(gpt_layernorm(dx, w.ln2_w, w.ln2_b, B, C, dln, nullptr, 0, s, g->pdl));
-    if (fs) {
+    static const bool fc1_fullk = getenv("MGV_FC1_FULLK") ? atoi(getenv("MGV_FC1_FULLK")) != 0 : true;
+    if (fc1_fullk && C % 256 == 0) {
+      // FC1 without split-K: bias + GELU fused into the epilogue, the separate GELU stage disappears
+      MGV_TRY(gemm_decode_fullk(w.wfc1, 4 * C, C, dln, B, w.bfc1, EPI_BF16_GELU, dh, nullptr, 4 * C, g->pdl, s));
+      g->launches += 1;
+    } else if (fs) {
       MGV_TRY(decode_gemm(g, dln, w.wfc1, w.bfc1, B, 4 * C, C, tl.fc1_split, EPI_F32, dh32, nullptr, s));
       MGV_TRY(gpt_gelu_bf16(dh32, static_cast<long long>(B) * 4 * C, dh, true, s, g->pdl));
       g->launches += 1;

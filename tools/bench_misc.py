@@ -46,3 +46,28 @@ for B in (64, 256):
 codes = torch.randint(0, 128, (64, 265)).to(dev)
 ms = timeit(lambda: vq.decode_codes(codes), n=3, warm=1)
 print("decode_to_img B=64: %.2f ms  %.0f clips/s  %.1f TFLOP/s (%.3f of peak)" % (ms, 64 / ms * 1e3, 261.3e9 * 64 / ms / 1e9, 261.3e9 * 64 / ms / 1e9 / TF))
+del vq
+torch.cuda.empty_cache()
+
+# ---- BASELINE config 1 on the GPU: one clip, 265 tokens (latency-bound: the same 8 stages per block at batch 1)
+lit = Lit_minGPT(args); lit.transformer.load_state_dict(synthetic.synthetic_gpt_state_dict(cfg, perturb=False), strict=False)
+lit = lit.eval().to(dev); lit.return_attention = False
+c1 = torch.tensor([[3]], device=dev); x1 = torch.zeros(1, 0, dtype=torch.long, device=dev)
+ms = timeit(lambda: lit.sample(x1, c1, steps=265, sample=True, top_k=100), n=3, warm=2)
+print("config 1 (one clip, 265 tokens, multinomial top_k=100): %.1f ms  %.0f tok/s  %.0f us/position" % (ms, 265 / ms * 1e3, ms * 1e3 / 265))
+del lit
+torch.cuda.empty_cache()
+
+# ---- BASELINE config 5: GPT-VAE (GPT-medium: vocab 1024, 24 layers, 1024-d latent), bs=128: encoder -> z -> decoder loss
+from melspec_gpt_vqvae_b200.transformer.Lit_GPT_VAE import GPT_VAE
+vargs = argparse.Namespace(embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, fix_var=-1.0, device=dev, kl_start=1.0,
+                           vocab_size=1024, block_size=265, n_layer=24, n_head=16, n_embd=1024)
+vae = GPT_VAE(vargs).eval().to(dev)
+xv = torch.randint(0, 1024, (128, 265), device=dev)
+ms = timeit(lambda: vae.loss(xv, 1.0, nsamples=1), n=3, warm=2)
+flv = 2 * (2 * 302.4e6 * 128 * 265) + 2 * 4 * 265 * 265 * 1024 * 24 * 128      # two 24-layer GPTs (encoder + decoder)
+print("config 5 GPT-VAE loss (encoder + reparameterise + decoder CE) bs=128: %.2f ms  %.0f clips/s  %.1f TFLOP/s (%.3f of peak)" % (ms, 128 / ms * 1e3, flv / ms / 1e9, flv / ms / 1e9 / TF))
+z = vae.sample_from_inference(xv[:64], 1)
+vae.decoder.return_attention = False      # like bench.py: the (B,16,T,T) attention map is an optional 288 MB by-product
+ms = timeit(lambda: vae.decode(z, "beam"), n=2, warm=1)
+print("config 5 GPT-VAE decode from latent bs=64 (265 tokens, top_k=100, vocab 1024): %.1f ms  %.0f tok/s" % (ms, 64 * 265 / ms * 1e3))
