@@ -524,7 +524,7 @@ int enqueue_group_step(Gpt* g, int b0, int B, const SampleArgs& sa, float* att_o
     MGV_TRY(decode_gemm(g, dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, dx, dx, s));
     MGV_TRY(gpt_layernorm(dx, w.ln2_w, w.ln2_b, B, C, dln, nullptr, 0, s, g->pdl));
     static const bool fc1_fullk = getenv("MGV_FC1_FULLK") ? atoi(getenv("MGV_FC1_FULLK")) != 0 : true;
-    if (fc1_fullk && C % 256 == 0) {
+    if (fc1_fullk && C % 256 == 0 && B > 32) {   // at most 32 sequences: 32 CTAs would stream 256 KB each (bs=1: 693 vs 591 us)
       // FC1 without split-K: bias + GELU fused into the epilogue, the separate GELU stage disappears
       MGV_TRY(gemm_decode_fullk(w.wfc1, 4 * C, C, dln, B, w.bfc1, EPI_BF16_GELU, dh, nullptr, 4 * C, g->pdl, s));
       g->launches += 1;
