@@ -432,41 +432,61 @@ norm_swish_conv_out_kernel(const __nv_bfloat16* __restrict__ h, const float* __r
 __global__ void __launch_bounds__(256)
 conv_in_1ch_kernel(const float* __restrict__ mel, const float* __restrict__ w, const float* __restrict__ bias, int N,
                    int H, int W, int Cout, uint4* __restrict__ out) {
-  extern __shared__ float ci_smem[];        // wt[9][Cout] | b[Cout]
-  float* wt = ci_smem;
-  float* bs = wt + 9 * Cout;
-  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
-    const int co = i % Cout, tap = i / Cout;
-    wt[i] = w[co * 9 + tap];
-  }
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias[i];
-  __syncthreads();
+  // A thread keeps the 9 x 8 weights of its 8 output channels in registers and walks over pixels; the C8 = Cout/8
+  // threads of a pixel are consecutive, so every store instruction writes whole pixels (Cout * 2 contiguous bytes).
+  // Pixel coordinates advance by carries, not divisions.  (First version: weights re-read from shared memory per tap
+  // and three 64-bit divisions per output vector -- 2.2 ms for 64 clips, 13 x the 0.17 ms its 1.1 GB of stores need.)
   const int C8 = Cout / 8;
-  const long long total = static_cast<long long>(N) * H * W * C8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(i % C8);
-    long long r = i / C8;
-    const int x = static_cast<int>(r % W);
-    r /= W;
-    const int y = static_cast<int>(r % H);
-    const long long n = r / H;
+  const int c8 = threadIdx.x % C8;                 // host guarantees blockDim % C8 == 0
+  float wr[9][8], bs[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    bs[e] = __ldg(bias + c8 * 8 + e);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) wr[tap][e] = __ldg(w + (c8 * 8 + e) * 9 + tap);
+  }
+  const int ppb = blockDim.x / C8;                 // pixels per block and iteration
+  const long long n_pix = static_cast<long long>(N) * H * W;
+  const long long step = static_cast<long long>(gridDim.x) * ppb;
+  long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / C8;
+  if (p >= n_pix) return;
+  int x = static_cast<int>(p % W);
+  long long r = p / W;
+  int y = static_cast<int>(r % H);
+  int n = static_cast<int>(r / H);
+  const int step_x = static_cast<int>(step % W);
+  const long long step_r = step / W;
+  const int step_y = static_cast<int>(step_r % H), step_n = static_cast<int>(step_r / H);
+  for (; p < n_pix; p += step) {
+    const float* base = mel + (static_cast<long long>(n) * H + y) * W + x;
     float acc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = bs[c8 * 8 + e];
+    for (int e = 0; e < 8; ++e) acc[e] = bs[e];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         const int yy = y + dy - 1, xx = x + dx - 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const float m = __ldg(mel + (n * H + yy) * W + xx);
-        const float* wr = wt + (dy * 3 + dx) * Cout + c8 * 8;
+        const float m = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(base + (dy - 1) * W + (dx - 1)) : 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(m, wr[e], acc[e]);
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(m, wr[dy * 3 + dx][e], acc[e]);
       }
-    out[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                        pack_bf16x2(acc[6], acc[7]));
+    out[p * C8 + c8] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                                  pack_bf16x2(acc[6], acc[7]));
+    // advance (x, y, n) by `step` pixels
+    x += step_x;
+    int cy = step_y;
+    if (x >= W) {
+      x -= W;
+      ++cy;
+    }
+    y += cy;
+    int cn = step_n;
+    if (y >= H) {
+      y -= H;
+      ++cn;
+    }
+    n += cn;
   }
 }
 
@@ -601,11 +621,14 @@ int vqvae_norm_swish_conv_out(const __nv_bfloat16* h, const float* sums, const f
 
 int vqvae_conv_in_1ch(const float* mel, const float* w, const float* bias, int N, int H, int W, int Cout,
                       __nv_bfloat16* out, cudaStream_t s) {
-  MGV_REQUIRE(Cout % 8 == 0 && Cout <= 512, "conv_in: Cout=%d", Cout);
-  const long long total = static_cast<long long>(N) * H * W * (Cout / 8);
-  if (total == 0) return MGV_OK;
-  const size_t smem = static_cast<size_t>(10) * Cout * 4;
-  conv_in_1ch_kernel<<<grid_for(total, 256), 256, smem, s>>>(mel, w, bias, N, H, W, Cout, reinterpret_cast<uint4*>(out));
+  MGV_REQUIRE(Cout % 8 == 0 && Cout <= 512 && 256 % (Cout / 8) == 0, "conv_in: Cout=%d", Cout);
+  const long long n_pix = static_cast<long long>(N) * H * W;
+  if (n_pix == 0) return MGV_OK;
+  const int ppb = 256 / (Cout / 8);
+  long long blocks = (n_pix + ppb - 1) / ppb;
+  const long long cap = static_cast<long long>(num_sms()) * 16;   // ~8 pixels per thread: the weight preload amortises
+  if (blocks > cap) blocks = cap;
+  conv_in_1ch_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(mel, w, bias, N, H, W, Cout, reinterpret_cast<uint4*>(out));
   MGV_CHECK_CUDA(cudaGetLastError());
   return MGV_OK;
 }
