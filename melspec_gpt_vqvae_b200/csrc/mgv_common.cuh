@@ -110,7 +110,8 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-__device__ __forceinline__ float swish(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x); fast division (rcp.approx + mul): the result is rounded to bf16 by every caller that stores it
+__device__ __forceinline__ float swish(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 #endif  // __CUDACC__
 
