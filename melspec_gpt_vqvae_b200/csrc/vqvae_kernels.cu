@@ -236,16 +236,36 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int N, int H, int
 }
 
 // ------------------------------------------------------------------ spatial self-attention (AttnBlock :434-446)
+// Single-head attention over the T = 5 x 53 latent positions with C = 512 channels, on the legacy tensor path
+// (mma.sync m16n8k16 bf16 -> fp32).  CTA = 32 query rows of one image, 8 warps.  Three phases over shared memory:
+//   scores   per 32-key chunk every warp owns one 16 x 8 tile of S = Q K^T (32 k-steps over the 512 channels),
+//   softmax  exact, over the full fp32 score rows (32 x T floats stay in shared memory),
+//   P V      per 32-key chunk every warp owns a 16-row x 128-channel slab of O (16 accumulator tiles), P converted
+//            to bf16 fragments on the fly, V fragments through ldmatrix.trans.
+// Rows are padded by 16 bytes (stride 1040 B): fragment loads and ldmatrix rows hit distinct banks.
+// (First version: the same structure on CUDA-core FMAs, 560 us per launch at 64 images.)
 constexpr int SA_ROWS = 32;
 constexpr int SA_KCH = 32;
 constexpr int SA_THREADS = 256;
 
+__device__ __forceinline__ void sa_mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void sa_ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r0), "=r"(r1)
+               : "r"(smem_u32(smem_row)));
+}
+
 template <int C>
 __global__ void __launch_bounds__(SA_THREADS)
 spatial_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bfloat16* __restrict__ o) {
-  constexpr int RS = C / 2 + 4;            // row stride in 32-bit words (16-byte aligned rows, conflict-free LDS.128)
+  constexpr int RS = C / 2 + 4;            // row stride in 32-bit words (16-byte aligned rows, conflict-free fragments)
   extern __shared__ __align__(16) uint32_t sa_smem[];
-  uint32_t* Qs = sa_smem;                  // [32][RS]
+  uint32_t* Qs = sa_smem;                  // [32][RS]  bf16 pairs
   uint32_t* KVs = Qs + SA_ROWS * RS;       // [32][RS]
   const int Tpad = ((T + SA_KCH - 1) / SA_KCH) * SA_KCH;
   const int SW = Tpad + 1;
@@ -254,6 +274,7 @@ spatial_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bfloat16*
   const int n = blockIdx.y;
   const int q0 = blockIdx.x * SA_ROWS;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, tq = lane & 3;  // mma fragment coordinates
   const __nv_bfloat16* base = qkv + static_cast<long long>(n) * T * (3 * C);
   constexpr int V8 = C / 8;                // uint4 per row
 
@@ -265,39 +286,42 @@ spatial_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bfloat16*
     *reinterpret_cast<uint4*>(Qs + r * RS + c8 * 4) = v;
   }
   const float scale = rsqrtf(static_cast<float>(C));   // int(c) ** (-0.5)   (:439)
-  const int qi = t >> 3, sub = t & 7;
   const int nchunks = Tpad / SA_KCH;
-
-  // ---- scores S = Q K^T * scale
-  for (int kc = 0; kc < nchunks; ++kc) {
-    __syncthreads();
+  auto load_chunk = [&](int kc, int col_off) {   // K (col_off = C) or V (2C) rows of chunk kc -> KVs, zero beyond T
     for (int i = t; i < SA_KCH * V8; i += SA_THREADS) {
       const int r = i / V8, c8 = i - r * V8;
       const int key = kc * SA_KCH + r;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (key < T) v = *reinterpret_cast<const uint4*>(base + static_cast<long long>(key) * (3 * C) + C + c8 * 8);
+      if (key < T) v = *reinterpret_cast<const uint4*>(base + static_cast<long long>(key) * (3 * C) + col_off + c8 * 8);
       *reinterpret_cast<uint4*>(KVs + r * RS + c8 * 4) = v;
     }
-    __syncthreads();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};   // keys sub, sub+8, sub+16, sub+24
-#pragma unroll 4
-    for (int w4 = 0; w4 < C / 8; ++w4) {
-      const uint4 qv = *reinterpret_cast<const uint4*>(Qs + qi * RS + w4 * 4);
-      const float2 qa = unpack_bf16x2(qv.x), qb = unpack_bf16x2(qv.y), qc = unpack_bf16x2(qv.z), qd = unpack_bf16x2(qv.w);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 kv = *reinterpret_cast<const uint4*>(KVs + (sub + 8 * j) * RS + w4 * 4);
-        const float2 ka = unpack_bf16x2(kv.x), kb = unpack_bf16x2(kv.y), kc2 = unpack_bf16x2(kv.z), kd = unpack_bf16x2(kv.w);
-        float a = acc[j];
-        a = fmaf(qa.x, ka.x, a); a = fmaf(qa.y, ka.y, a);
-        a = fmaf(qb.x, kb.x, a); a = fmaf(qb.y, kb.y, a);
-        a = fmaf(qc.x, kc2.x, a); a = fmaf(qc.y, kc2.y, a);
-        a = fmaf(qd.x, kd.x, a); a = fmaf(qd.y, kd.y, a);
-        acc[j] = a;
+  };
+
+  // ---- scores S = Q K^T * scale: warp -> query rows 16*(warp & 1) .. +15, keys 8*(warp >> 1) .. +7 of the chunk
+  {
+    const int mrow = (warp & 1) * 16, ncol = (warp >> 1) * 8;
+    for (int kc = 0; kc < nchunks; ++kc) {
+      __syncthreads();
+      load_chunk(kc, C);
+      __syncthreads();
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t* qa = Qs + (mrow + g) * RS + tq;
+      const uint32_t* kb = KVs + (ncol + g) * RS + tq;
+#pragma unroll 8
+      for (int ks = 0; ks < C / 16; ++ks) {          // 16 channels = 8 words per step
+        uint32_t a[4];
+        a[0] = qa[ks * 8];
+        a[1] = qa[8 * RS + ks * 8];
+        a[2] = qa[ks * 8 + 4];
+        a[3] = qa[8 * RS + ks * 8 + 4];
+        sa_mma_16816(acc, a, kb[ks * 8], kb[ks * 8 + 4]);
       }
+      float* s0 = Ss + (mrow + g) * SW + kc * SA_KCH + ncol + tq * 2;
+      s0[0] = acc[0] * scale;
+      s0[1] = acc[1] * scale;
+      s0[8 * SW] = acc[2] * scale;
+      s0[8 * SW + 1] = acc[3] * scale;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Ss[qi * SW + kc * SA_KCH + sub + 8 * j] = acc[j] * scale;
   }
   __syncthreads();
 
@@ -318,44 +342,40 @@ spatial_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int T, __nv_bfloat16*
     for (int k = lane; k < Tpad; k += 32) row[k] *= inv;
   }
 
-  // ---- O = P V ; thread -> row qi, dims {i*64 + sub*8 .. +7}
-  float oacc[C / 8];
+  // ---- O = P V: warp -> query rows 16*(warp & 1) .. +15, channels 128*(warp >> 1) .. +127 (16 tiles of 8)
+  const int mrow = (warp & 1) * 16, cbase = (warp >> 1) * (C / 4);
+  float oacc[C / 32][4];
 #pragma unroll
-  for (int e = 0; e < C / 8; ++e) oacc[e] = 0.f;
+  for (int i = 0; i < C / 32; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
   for (int kc = 0; kc < nchunks; ++kc) {
     __syncthreads();
-    for (int i = t; i < SA_KCH * V8; i += SA_THREADS) {
-      const int r = i / V8, c8 = i - r * V8;
-      const int key = kc * SA_KCH + r;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (key < T) v = *reinterpret_cast<const uint4*>(base + static_cast<long long>(key) * (3 * C) + 2 * C + c8 * 8);
-      *reinterpret_cast<uint4*>(KVs + r * RS + c8 * 4) = v;
-    }
+    load_chunk(kc, 2 * C);
     __syncthreads();
-    for (int kk = 0; kk < SA_KCH; ++kk) {
-      const float p = Ss[qi * SW + kc * SA_KCH + kk];
 #pragma unroll
-      for (int i = 0; i < C / 64; ++i) {
-        const uint4 vv = *reinterpret_cast<const uint4*>(KVs + kk * RS + i * 32 + sub * 4);
-        const float2 a = unpack_bf16x2(vv.x), b = unpack_bf16x2(vv.y), c = unpack_bf16x2(vv.z), d = unpack_bf16x2(vv.w);
-        oacc[i * 8 + 0] = fmaf(p, a.x, oacc[i * 8 + 0]);
-        oacc[i * 8 + 1] = fmaf(p, a.y, oacc[i * 8 + 1]);
-        oacc[i * 8 + 2] = fmaf(p, b.x, oacc[i * 8 + 2]);
-        oacc[i * 8 + 3] = fmaf(p, b.y, oacc[i * 8 + 3]);
-        oacc[i * 8 + 4] = fmaf(p, c.x, oacc[i * 8 + 4]);
-        oacc[i * 8 + 5] = fmaf(p, c.y, oacc[i * 8 + 5]);
-        oacc[i * 8 + 6] = fmaf(p, d.x, oacc[i * 8 + 6]);
-        oacc[i * 8 + 7] = fmaf(p, d.y, oacc[i * 8 + 7]);
+    for (int ks = 0; ks < SA_KCH / 16; ++ks) {       // 16 keys per step
+      const float* p0 = Ss + (mrow + g) * SW + kc * SA_KCH + ks * 16 + tq * 2;
+      uint32_t a[4];
+      a[0] = pack_bf16x2(p0[0], p0[1]);
+      a[1] = pack_bf16x2(p0[8 * SW], p0[8 * SW + 1]);
+      a[2] = pack_bf16x2(p0[8], p0[9]);
+      a[3] = pack_bf16x2(p0[8 * SW + 8], p0[8 * SW + 9]);
+      const uint32_t* vrow = KVs + (ks * 16 + (lane & 15)) * RS + cbase / 2;
+#pragma unroll
+      for (int i = 0; i < C / 32; ++i) {
+        uint32_t b0, b1;
+        sa_ldmatrix_x2_trans(b0, b1, vrow + i * 4);
+        sa_mma_16816(oacc[i], a, b0, b1);
       }
     }
   }
-  if (q0 + qi < T) {
-    __nv_bfloat16* orow = o + (static_cast<long long>(n) * T + q0 + qi) * C;
+  const int r0 = q0 + mrow + g, r1 = r0 + 8;
 #pragma unroll
-    for (int i = 0; i < C / 64; ++i)
-      *reinterpret_cast<uint4*>(orow + i * 64 + sub * 8) =
-          make_uint4(pack_bf16x2(oacc[i * 8 + 0], oacc[i * 8 + 1]), pack_bf16x2(oacc[i * 8 + 2], oacc[i * 8 + 3]),
-                     pack_bf16x2(oacc[i * 8 + 4], oacc[i * 8 + 5]), pack_bf16x2(oacc[i * 8 + 6], oacc[i * 8 + 7]));
+  for (int i = 0; i < C / 32; ++i) {
+    const int ch = cbase + i * 8 + tq * 2;
+    if (r0 < T)
+      *reinterpret_cast<uint32_t*>(o + (static_cast<long long>(n) * T + r0) * C + ch) = pack_bf16x2(oacc[i][0], oacc[i][1]);
+    if (r1 < T)
+      *reinterpret_cast<uint32_t*>(o + (static_cast<long long>(n) * T + r1) * C + ch) = pack_bf16x2(oacc[i][2], oacc[i][3]);
   }
 }
 
