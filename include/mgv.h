@@ -49,7 +49,8 @@ int mgv_device_check(void);
 
 /* VectorQuantizer.forward, index part  (vqvae/big_model_attn_gan.py:19-33).
  * z_bchw: fp32 (B, C, H*W) -- the encoder output as is (no BHWC permute needed);
- * codebook: fp32 (K, C) = _embedding.weight;  K <= 128, C in {64,128,192,256};
+ * codebook: fp32 (K, C) = _embedding.weight;  C in {64,128,192,256};  K up to 65536: codebooks beyond 128 codes
+ *   (e.g. the reference's 1024-code VGGSound variant) are searched in passes of 128 codes, lowest index still wins;
  * idx_out: int64 (B*H*W) in (b, h, w) order (= encoding_indices.squeeze(1));
  * dmin_out: optional fp32 (B*H*W), the winning distance.
  * Distances are fp32, d = (|x|^2 + |e|^2) - 2<x,e>, every sum a sequential fmaf chain over

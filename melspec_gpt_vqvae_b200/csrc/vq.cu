@@ -40,7 +40,11 @@ __device__ __forceinline__ void cp_async_wait() {
 // dynamic smem: es[D][128] | ee[128] | xs[2][VQ_KC][128]
 __global__ void __launch_bounds__(VQ_THREADS, 1)
 vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ codebook, int B, int D, int HW, int K,
-                 long long* __restrict__ idx_out, float* __restrict__ dmin_out) {
+                 long long* __restrict__ idx_out, float* __restrict__ dmin_out, int code0, int merge) {
+  // Codebooks larger than the 128-code register tiling run as passes over chunks of 128 codes (code0 = first code of
+  // this pass, ascending): a pass with merge = 1 keeps the earlier passes' winner unless its own minimum is strictly
+  // smaller, which preserves "lowest index wins" across chunks.  K counts the codes of THIS chunk.
+  codebook += static_cast<size_t>(code0) * D;
   extern __shared__ __align__(16) float vq_smem[];
   float* es = vq_smem;                        // [D][128]
   float* ee = es + static_cast<size_t>(D) * VQ_MAX_K;  // [128]
@@ -171,8 +175,11 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ codebook
       }
       const long long n = n0 + vg * 8 + i;
       if (cg == 0 && n < N) {
-        idx_out[n] = bi;
-        if (dmin_out) dmin_out[n] = best;
+        const bool keep_old = merge && !(best < dmin_out[n]);
+        if (!keep_old) {
+          idx_out[n] = code0 + bi;
+          if (dmin_out) dmin_out[n] = best;
+        }
       }
     }
   }
@@ -276,14 +283,19 @@ __global__ void vq_gather_kernel(const long long* __restrict__ idx, const float*
 
 }  // namespace
 
+namespace {
+// scratch for the running minimum distance of multi-pass (K > 128) searches when the caller passes no dmin buffer
+float* g_dmin_scratch = nullptr;
+long long g_dmin_cap = 0;
+}  // namespace
+
 int vq_argmin(const float* z, const float* codebook, int B, int D, int HW, int K, long long* idx_out, float* dmin_out,
               cudaStream_t stream) {
   MGV_REQUIRE(B >= 0 && HW > 0, "vq_argmin: B=%d HW=%d", B, HW);
   if (B == 0) return MGV_OK;   // empty batch: nothing to do (pointers may be null)
   MGV_REQUIRE(z && codebook && idx_out, "vq_argmin: null pointer");
-  MGV_REQUIRE(K >= 1 && K <= VQ_MAX_K, "vq_argmin: num_embeddings=%d unsupported (1..%d)", K, VQ_MAX_K);
+  MGV_REQUIRE(K >= 1 && K <= 65536, "vq_argmin: num_embeddings=%d unsupported (1..65536)", K);
   MGV_REQUIRE(D >= VQ_KC && D % VQ_KC == 0 && D <= 256, "vq_argmin: embedding_dim=%d must be 64, 128, 192 or 256", D);
-  if (B == 0) return MGV_OK;
   const long long N = static_cast<long long>(B) * HW;
   const int num_tiles = static_cast<int>((N + VQ_TILE_V - 1) / VQ_TILE_V);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
@@ -293,8 +305,24 @@ int vq_argmin(const float* z, const float* codebook, int B, int D, int HW, int K
     MGV_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  vq_argmin_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, codebook, B, D, HW, K, idx_out, dmin_out);
-  MGV_CHECK_CUDA(cudaGetLastError());
+  if (K > VQ_MAX_K && dmin_out == nullptr) {   // the passes hand the running minimum to each other
+    if (g_dmin_cap < N) {
+      if (g_dmin_scratch) {
+        MGV_CHECK_CUDA(cudaStreamSynchronize(stream));   // (rare: growth only) earlier launches may still use the old block
+        cudaFree(g_dmin_scratch);
+        g_dmin_scratch = nullptr;
+        g_dmin_cap = 0;
+      }
+      MGV_CHECK_CUDA(cudaMalloc(&g_dmin_scratch, static_cast<size_t>(N) * sizeof(float)));
+      g_dmin_cap = N;
+    }
+    dmin_out = g_dmin_scratch;
+  }
+  for (int code0 = 0; code0 < K; code0 += VQ_MAX_K) {
+    const int kc = (K - code0 < VQ_MAX_K) ? K - code0 : VQ_MAX_K;
+    vq_argmin_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, codebook, B, D, HW, kc, idx_out, dmin_out, code0, code0 > 0 ? 1 : 0);
+    MGV_CHECK_CUDA(cudaGetLastError());
+  }
   return MGV_OK;
 }
 

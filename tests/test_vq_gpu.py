@@ -110,3 +110,25 @@ def test_vq_edge_cases():
         m(torch.zeros(1, 256, 5, 53))
     with pytest.raises(RuntimeError):
         m.cpu()(torch.zeros(1, 256, 5, 53, device="cuda"))
+
+
+@pytest.mark.parametrize("K", [129, 300, 1024])
+def test_vq_large_codebooks_multi_pass(K):
+    """Codebooks beyond the 128-code register tiling (the reference's 1024-code VGGSound variant, README.md:182) run as
+    passes over 128-code chunks: indices stay bit-exact, ties across chunks still go to the lowest index."""
+    g = torch.Generator().manual_seed(K)
+    cb = torch.randn(K, 256, generator=g) * 0.2
+    cb[K - 1] = cb[3]            # duplicate code in the last chunk: index 3 must win
+    cb[130 % K] = cb[5] if K > 130 else cb[130 % K]
+    z = torch.randn(4, 256, 5, 53, generator=g) * 0.2
+    z[0, :, 0, 0] = cb[3]        # a vector equal to the duplicated code
+    m = _vq(K, 256, cb)
+    loss, quant, (perp, enc, idx) = m(z.cuda())
+    o_idx, _ = vq_oracle.argmin_exact(z.numpy(), cb.numpy())
+    assert np.array_equal(idx.cpu().numpy().reshape(-1), o_idx)
+    assert int(idx[0]) == 3
+    r_loss, r_quant, (r_perp, r_enc, r_idx) = vq_oracle.forward_numpy(z.numpy(), cb.numpy(), 0.25, indices=o_idx)
+    np.testing.assert_allclose(float(loss), float(r_loss), rtol=1e-5)
+    np.testing.assert_allclose(float(perp), float(r_perp), rtol=1e-4)
+    assert enc.shape == (4 * 265, K) and float(enc.sum()) == 4 * 265
+    np.testing.assert_array_equal(quant.cpu().numpy(), r_quant)
