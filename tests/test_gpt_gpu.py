@@ -225,3 +225,29 @@ def test_generate_batch_sizes_beyond_one_tile(B):
     agree = float((xs[-5:] == ref).float().mean())
     print("B=%d vs B=5 greedy agreement on the last 5 sequences: %.3f" % (B, agree))
     assert agree > 0.9
+
+
+def test_odd_head_count_config_vs_oracle():
+    """Shapes that are not powers of two (the reference's GPT-XL GPT-VAE variant has 23 heads x 64 = 1472 channels,
+    config_GPT_VAE_vggsound.py:43-59): 3 heads x 64 = 192 channels, vocab 96, compared with the fp32 oracle directly."""
+    cfg = dict(vocab_size=96, block_size=70, n_layer=2, n_head=3, n_embd=192, class_size=5, n_unmasked=0, last_linear=None)
+    sd = synthetic.synthetic_gpt_state_dict(cfg, seed=77, perturb=True)
+    m = make_gpt(cfg, sd)
+    x, c = gpt_inputs(5, 60, 96, 5, seed=3)
+    logits, _, att = m(x.cuda(), c.cuda())
+    ocfg = gpt_oracle.GPTCfg(**cfg)
+    o_logits, _, o_att = gpt_oracle.gptclass_forward(sd, ocfg, x, c)
+    emax, erms = err_stats(logits.cpu(), o_logits)
+    print("3-head config logits err max %.4f rms %.4f" % (emax, erms))
+    assert emax <= LOGIT_TOL_MAX and erms <= LOGIT_TOL_RMS
+    assert err_stats(att.cpu(), o_att)[0] <= ATT_TOL
+    # greedy generation through the decode loop (split-K tilings with ragged tile / k-block counts) vs the oracle loop
+    sd2 = dict(sd)
+    sd2["head.weight"] = sd["head.weight"] * 8.0
+    lit = _lit(cfg, sd2)
+    lit.return_attention = False
+    xs, _ = lit.sample(torch.zeros(5, 0, dtype=torch.long, device="cuda"), c.cuda(), steps=40, sample=False)
+    o_xs, _ = gpt_oracle.sample(sd2, ocfg, torch.zeros(5, 0, dtype=torch.long), c, steps=40)
+    agree = float((xs.cpu() == o_xs).float().mean())
+    print("3-head config greedy agreement with the oracle: %.3f" % agree)
+    assert agree > 0.9
