@@ -51,27 +51,38 @@ struct KParams {
 // contiguous bytes (16 full sectors).  "own" = lane l holds the 64 bytes of row l; "spread" = instruction i of lane l
 // holds 16-byte piece (l & 3) of row 8*i + (l >> 2).  The XOR keeps both access patterns bank-conflict free.
 constexpr int EPI_STAGE_BYTES = 32 * 64;
-__device__ __forceinline__ uint8_t* stage_own(uint8_t* buf, int lane, int j) {
+// explicit shared-space accesses (through a generic pointer parameter the compiler emits generic ST.E / LD.E)
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t stage_own(uint32_t buf, int lane, int j) {
   return buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
 }
-__device__ __forceinline__ uint8_t* stage_spread(uint8_t* buf, int lane, int i) {
+__device__ __forceinline__ uint32_t stage_spread(uint32_t buf, int lane, int i) {
   const int r = 8 * i + (lane >> 2), c = lane & 3;
   return buf + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
 }
-__device__ __forceinline__ void own_to_spread(uint8_t* buf, int lane, const uint4 (&in)[4], uint4 (&out)[4]) {
+__device__ __forceinline__ void own_to_spread(uint8_t* stage, int lane, const uint4 (&in)[4], uint4 (&out)[4]) {
+  const uint32_t buf = smem_u32(stage);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stage_own(buf, lane, j)) = in[j];
+  for (int j = 0; j < 4; ++j) sts_v4(stage_own(buf, lane, j), in[j]);
   __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) out[i] = *reinterpret_cast<const uint4*>(stage_spread(buf, lane, i));
+  for (int i = 0; i < 4; ++i) out[i] = lds_v4(stage_spread(buf, lane, i));
   __syncwarp();
 }
-__device__ __forceinline__ void spread_to_own(uint8_t* buf, int lane, const uint4 (&in)[4], uint4 (&out)[4]) {
+__device__ __forceinline__ void spread_to_own(uint8_t* stage, int lane, const uint4 (&in)[4], uint4 (&out)[4]) {
+  const uint32_t buf = smem_u32(stage);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage_spread(buf, lane, i)) = in[i];
+  for (int i = 0; i < 4; ++i) sts_v4(stage_spread(buf, lane, i), in[i]);
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) out[j] = *reinterpret_cast<const uint4*>(stage_own(buf, lane, j));
+  for (int j = 0; j < 4; ++j) out[j] = lds_v4(stage_own(buf, lane, j));
   __syncwarp();
 }
 
