@@ -132,6 +132,23 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ensure_library(local_rank):
+    """libmgv.so normally arrives prebuilt with the snapshot; if it does not, local rank 0 compiles it (nvcc, sm_100a)
+    and the other ranks wait for it.  The product itself never builds or falls back: a missing library raises."""
+    from melspec_gpt_vqvae_b200 import build as b
+    if os.path.isfile(b.LIB_PATH):
+        return
+    if local_rank == 0:
+        b.build(verbose=False)
+        return
+    t0 = time.time()
+    while not os.path.isfile(b.LIB_PATH):
+        if time.time() - t0 > 900:
+            raise RuntimeError("bench.py: libmgv.so did not appear (local rank 0 builds it)")
+        time.sleep(1.0)
+    time.sleep(2.0)   # let the linker finish writing
+
+
 def build_models(device):
     import argparse as ap
     from melspec_gpt_vqvae_b200 import synthetic
@@ -158,6 +175,7 @@ def run_ours(a):
         raise RuntimeError("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    ensure_library(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lit, cfg = build_models(device)
