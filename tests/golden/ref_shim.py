@@ -95,7 +95,7 @@ def import_reference():
     # make sure we get the reference's top-level packages, not ours
     for name in ("vqvae", "transformer"):
         m = sys.modules.get(name)
-        if m is not None and not getattr(m, "__file__", "").startswith(REF_ROOT) and \
+        if m is not None and not (getattr(m, "__file__", None) or "").startswith(REF_ROOT) and \
                 not any(str(p).startswith(REF_ROOT) for p in getattr(m, "__path__", [])):
             del sys.modules[name]
     cwd = os.getcwd()
