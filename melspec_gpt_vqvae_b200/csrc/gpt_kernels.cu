@@ -139,7 +139,7 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 }
 
 template <bool WRITE_ATT>
-__global__ void __launch_bounds__(FA_THREADS)
+__global__ void __launch_bounds__(FA_THREADS, 2)   // two CTAs per SM (92 KB of smem each): <= 113 registers
 attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int T, int nh, int n_unmasked,
                     __nv_bfloat16* __restrict__ y, float* __restrict__ att, int att_T,
                     __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache, int Tmax) {
