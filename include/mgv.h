@@ -170,11 +170,17 @@ int mgv_test_gemm(int impl, const void* A, const void* B, int M, int N, int K, i
 int mgv_test_gemm_swapab(int impl, const void* W, const void* X, int M, int N, int K, int epi, const float* bias,
                          void* out, const void* resid, int bn, int split_k, mgv_stream_t stream);
 
-/* Fused decode GEMMs: out[b, n] += sum_k act(src)[b, k] * W[n, k] + bias[n]; mode 0: act = gelu_erf,
- * mode 1: act = LayerNorm(gamma, beta, eps 1e-5) with the row statistics exchanged between the split-K CTAs of a
- * thread-block cluster.  W bf16 (Nw, K); src fp32 (B, K), B <= 64; out fp32 (B, Nw) accumulated in place. */
-int mgv_test_gemm_fused(int mode, const void* W, const float* src, int Nw, int B, int K, const float* gamma,
-                        const float* beta, const float* bias, float* out, int split_k, mgv_stream_t stream);
+/* Decode GEMMs that absorb the LayerNorm / GELU in front of them (gemm_decode_fold.cu; reference math:
+ * transformer/minGPT.py:100-119, 186-188).  W bf16 (Nw, K); src fp32 (B, K); out fp32 (B, Nw), accumulated in place.
+ * mode 0: out += LayerNorm(src; gamma, beta, eps 1e-5) W^T + bias, computed as the folded form the decode chain uses
+ *         (raw W bf16(gamma.src) accumulation + per-K-slice row statistics, then rstd * (acc - mu * W gamma) + W beta + bias);
+ *         out must hold zeros.  gamma_or_sw = gamma (K), beta_or_bp = beta (K).
+ * mode 1: out += gelu_erf(rstd_b * (src - mu_b * sw) + bp) W^T + bias with mu / rstd from stats_in (nparts, B, 2) =
+ *         partial (sum, sum of squares) over ln_dim elements.  gamma_or_sw = sw (K), beta_or_bp = bp (K).
+ * kbps = 64-wide k-blocks per CTA (1..4); staging_warps = 4 or 8, plus 100 to select 64 sequences per CTA (default 32). */
+int mgv_test_gemm_fold(int mode, const void* W, const float* src, int Nw, int B, int K, const float* gamma_or_sw,
+                       const float* beta_or_bp, const float* bias, const float* stats_in, int nparts, int ln_dim,
+                       float* out, int kbps, int staging_warps, mgv_stream_t stream);
 
 /* 3x3 convolution (stride 1 pad 1, or stride 2 with the reference's (0,1,0,1) padding) over
  * NHWC bf16 input through the implicit-GEMM path (impl 0) or the SIMT reference (impl 1).

@@ -43,7 +43,7 @@ SIGNATURES = {
     "mgv_vqvae_last_launches": (I64, [VP]),
     "mgv_test_gemm": (I, [I, VP, VP, I, I, I, I, VP, VP, VP, I, I, VP]),
     "mgv_test_gemm_swapab": (I, [I, VP, VP, I, I, I, I, VP, VP, VP, I, I, VP]),
-    "mgv_test_gemm_fused": (I, [I, VP, VP, I, I, I, VP, VP, VP, VP, I, VP]),
+    "mgv_test_gemm_fold": (I, [I, VP, VP, I, I, I, VP, VP, VP, VP, I, I, VP, I, I, VP]),
     "mgv_test_conv3x3": (I, [I, VP, VP, VP, I, I, I, I, I, I, VP, VP, VP]),
 }
 

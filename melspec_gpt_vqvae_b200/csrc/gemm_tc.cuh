@@ -63,18 +63,36 @@ struct GemmArgs {
 
 int gemm_bf16_tc(const GemmArgs& a);
 
-// Decode-step GEMMs with the activation operand produced in-kernel (gemm_decode_fused.cu):
-//   out[b, n] += sum_k act(src)[b, k] * W[n, k] (+ bias[n])   with act = gelu_erf or LayerNorm(gamma, beta, eps 1e-5).
-// W bf16 [Nw, K]; src fp32 [B, K]; out fp32 [B, ldo] accumulated with atomics (must hold the residual / zeros); B <= 64.
-int gemm_decode_gelu(const void* W, int Nw, int K, const float* src_f32, int B, const float* bias, float* out, long long ldo,
-                     int split_k, bool pdl, cudaStream_t stream);
-int gemm_decode_ln(const void* W, int Nw, int K, const float* x_f32, int B, const float* gamma, const float* beta,
-                   const float* bias, float* out, long long ldo, int split_k, bool pdl, cudaStream_t stream);
-
 // Decode-step GEMM without split-K (gemm_decode_fullk.cu): a CTA = 128 weight rows x 32 sequences x all of K;
 // epi in {EPI_BF16_GELU, EPI_F32, EPI_F32_RESID}; W bf16 [Nw, K], X bf16 [B, K], K % 256 == 0.
 int gemm_decode_fullk(const void* W, int Nw, int K, const void* X_bf16, int B, const float* bias, int epi, void* out,
                       const void* resid, long long ldo, bool pdl, cudaStream_t stream);
+
+// ---- decode-step GEMMs that absorb the LayerNorm / GELU stage in front of them (gemm_decode_fold.cu)
+// (LnFold: mgv_common.cuh)
+enum FoldMode : int { FOLD_LN = 0, FOLD_GELU = 1 };
+// L2 prefetch request carried by a fold GEMM: rows [0, *pos_ptr) of `pairs` (sequence, head) runs of the K and the V cache
+struct KvPrefetch {
+  const char* k = nullptr;
+  const char* v = nullptr;
+  const int* pos_ptr = nullptr;
+  int pairs = 0;
+  unsigned row_bytes = 0;          // bytes of one cache row (head dim * 2)
+  long long run_stride = 0;        // bytes between two (sequence, head) runs
+};
+// mode FOLD_LN  : out[b, n] += sum_k W[n,k] bf16(gamma[k] src[b,k]);  stats_out[z][b] = partial row statistics of src
+// mode FOLD_GELU: out[b, n] += sum_k W[n,k] bf16(gelu(rstd_b (src[b,k] - mu_b in.sw[k]) + in.bp[k])) (+ bias[n])
+// W bf16 [Nw, K]; src fp32 [B, K]; out fp32 [B, ldo] (holds zeros / the residual); kbps = 64-wide k-blocks per CTA (<= 4);
+// bn = sequences per CTA (32 or 64).
+int gemm_decode_fold(int mode, const void* W, int Nw, int K, const float* src, int B, const float* gamma,
+                     float2* stats_out, int stats_stride, const LnFold* in, const float* bias, float* out, long long ldo,
+                     int kbps, int staging_warps, int bn, bool pdl, cudaStream_t stream, const KvPrefetch* pf = nullptr);
+// sw[n] = sum_k W[n,k] gamma[k];  bp[n] = sum_k W[n,k] beta[k] + bias[n] (bias may be null)
+int gpt_fold_prepare(const void* W, int N, int K, const float* gamma, const float* beta, const float* bias, float* sw,
+                     float* bp, cudaStream_t stream);
+
+// out[b, n] = rstd_b * (out[b, n] - mu_b * f.sw[n]) + f.bp[n]: the consumer-side half of FOLD_LN as a stand-alone kernel (tests)
+int gpt_fold_apply(float* out, int B, int N, const LnFold& f, cudaStream_t stream);
 
 // SIMT fp32 reference of the same contract (tests / on-device cross-checks only).
 int gemm_bf16_ref(const GemmArgs& a);

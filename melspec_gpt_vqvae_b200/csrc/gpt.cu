@@ -7,7 +7,6 @@
 #include "gemm_tc.cuh"
 #include "gpt_kernels.cuh"
 #include "gpt.cuh"
-#include "gpt_decode_program.cuh"
 
 namespace mgv {
 
@@ -41,6 +40,8 @@ struct GptLayer {
   float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
   __nv_bfloat16 *wqkv, *wproj, *wfc1, *wfc2;
   float *bqkv, *bproj, *bfc1, *bfc2;
+  // folded-LayerNorm vectors of the decode chain (gemm_decode_fold.cu): sw = W gamma, bp = W beta + b
+  float *sw_qkv, *bp_qkv, *sw_fc1, *bp_fc1;
 };
 
 // split-K factors of the decode-step GEMMs (swap-AB: 128 weight rows per CTA x split-K slices)
@@ -51,6 +52,8 @@ struct DecodeTiles {
   int fc2_split = 16;   //  8 row tiles x 16 = 128 CTAs
   int head_split = 16;  //  1 row tile  x 16 (vocab 128)
 };
+
+constexpr int FOLD_MAX_PARTS = 64;
 
 struct Gpt {
   GptConfig cfg;
@@ -85,16 +88,16 @@ struct Gpt {
   static constexpr int MAX_GROUPS = 8;
   int groups = 1;   // MGV_DECODE_GROUPS: measured 935 (2 groups) vs 1016 us per position, but every chain still pays the
                     // full per-stage latency, and the default stays one group (deterministic launch order, simpler graph)
-  // Stage-program decode path (gpt_decode_program.cu, opt-in with MGV_DECODE_PROGRAM=1): per block one persistent
-  // kernel runs proj -> LN2 -> FC1+GELU -> FC2 -> LN1' -> QKV' with grid barriers instead of kernel boundaries.
-  // Correct (same tests), measured slower than the PDL chain (1215 vs 1016 us per position): see DESIGN.md section 7.
-  bool use_program = false;
-  DecStage* d_prog = nullptr;
-  CUtensorMap* d_maps = nullptr;
-  unsigned int* d_counters = nullptr;
-  unsigned long long* d_trace = nullptr;           // MGV_DP_TRACE=1: per-kernel stage timestamps (diagnostics)
-  int prog_B = 0;                                  // batch the program was built for (0 = none)
-  std::vector<std::pair<int, int>> prog_ranges;    // stage range of each program kernel of one position
+  // Folded decode chain (default): LayerNorm / GELU are applied by the consumer of each split-K accumulator, so a
+  // block is 5 dependent kernels (QKV, attention, proj, FC1, FC2) instead of 7.  MGV_DECODE_FOLD=0 selects the
+  // separate-LayerNorm chain (also used for shapes the fold kernels do not cover).
+  bool use_fold = true;
+  bool fold_dirty = true;          // sw / bp vectors must be recomputed (a weight was loaded)
+  float *sw_head = nullptr, *bp_head = nullptr;
+  float2 *stats1 = nullptr, *stats2 = nullptr;   // [FOLD_MAX_PARTS][dec_B] partial LayerNorm statistics (ln1 / ln_f, ln2)
+  int fold_sw = 4, fold_sw_gelu = 8;             // staging warps of the fold GEMMs (MGV_FOLD_SW=a,b)
+  bool kv_prefetch = true;                       // MGV_KV_PREFETCH=0: no L2 prefetch of the next layer's KV rows
+  int fold_bn = 32, fold_bn2 = 32;               // sequences per CTA of the FOLD_LN / FOLD_GELU GEMMs (MGV_FOLD_BN=a,b)
   cudaStream_t gstream[MAX_GROUPS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {};
   bool pdl = false;
@@ -133,6 +136,8 @@ void carve_params(Gpt* g, char* base, size_t* total) {
   g->lnf_w = c.take<float>(C);
   g->lnf_b = c.take<float>(C);
   g->whead = c.take<__nv_bfloat16>(static_cast<size_t>(g->Vout) * C);
+  g->sw_head = c.take<float>(g->Vout);
+  g->bp_head = c.take<float>(g->Vout);
   g->layers.resize(g->L);
   for (int l = 0; l < g->L; ++l) {
     GptLayer& y = g->layers[l];
@@ -148,6 +153,10 @@ void carve_params(Gpt* g, char* base, size_t* total) {
     y.bfc1 = c.take<float>(4 * C);
     y.wfc2 = c.take<__nv_bfloat16>(4 * C * C);
     y.bfc2 = c.take<float>(C);
+    y.sw_qkv = c.take<float>(3 * C);
+    y.bp_qkv = c.take<float>(3 * C);
+    y.sw_fc1 = c.take<float>(4 * C);
+    y.bp_fc1 = c.take<float>(4 * C);
   }
   *total = c.off;
 }
@@ -170,9 +179,9 @@ int ensure_prefill_ws(Gpt* g, int rows) {
 int ensure_decode_ws(Gpt* g, int B) {
   if (B <= g->dec_B) return MGV_OK;
   cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
-  cudaFree(g->kv); cudaFree(g->dlogits); cudaFree(g->dtokens);
+  cudaFree(g->kv); cudaFree(g->dlogits); cudaFree(g->dtokens); cudaFree(g->stats1); cudaFree(g->stats2);
   g->dtokens = nullptr;
-  g->prog_B = 0;
+  g->stats1 = g->stats2 = nullptr;
   if (g->graph_exec) { cudaGraphExecDestroy(g->graph_exec); g->graph_exec = nullptr; }
   if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }
   g->dx = g->dqkv32 = g->dh32 = g->dlogits = nullptr;
@@ -189,6 +198,8 @@ int ensure_decode_ws(Gpt* g, int B) {
   MGV_CHECK_CUDA(cudaMalloc(&g->dh, R * 4 * C * 2));
   const size_t kv_elems = static_cast<size_t>(g->L) * 2 * R * g->nh * g->Tmax * GPT_HEAD_DIM;
   MGV_CHECK_CUDA(cudaMalloc(&g->kv, kv_elems * 2));
+  MGV_CHECK_CUDA(cudaMalloc(&g->stats1, static_cast<size_t>(FOLD_MAX_PARTS) * R * sizeof(float2)));
+  MGV_CHECK_CUDA(cudaMalloc(&g->stats2, static_cast<size_t>(FOLD_MAX_PARTS) * R * sizeof(float2)));
   g->dec_B = B;
   return MGV_OK;
 }
@@ -298,8 +309,20 @@ int gpt_create(const GptConfig* cfg, Gpt** out) {
     cudaStreamCreateWithFlags(&g->gstream[c], cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&g->ev_join[c], cudaEventDisableTiming);
   }
-  const char* pe = getenv("MGV_DECODE_PROGRAM");
-  if (pe) g->use_program = atoi(pe) != 0;
+  const char* fe = getenv("MGV_DECODE_FOLD");
+  if (fe) g->use_fold = atoi(fe) != 0;
+  const char* kp = getenv("MGV_KV_PREFETCH");
+  if (kp) g->kv_prefetch = atoi(kp) != 0;
+  const char* fb = getenv("MGV_FOLD_BN");
+  if (fb) {
+    int a = 0, b = 0;
+    if (sscanf(fb, "%d,%d", &a, &b) == 2 && (a == 32 || a == 64) && (b == 32 || b == 64)) { g->fold_bn = a; g->fold_bn2 = b; }
+  }
+  const char* fw = getenv("MGV_FOLD_SW");
+  if (fw) {
+    int a = 0, b = 0;
+    if (sscanf(fw, "%d,%d", &a, &b) == 2 && (a == 4 || a == 8) && (b == 4 || b == 8)) { g->fold_sw = a; g->fold_sw_gelu = b; }
+  }
   const char* ge = getenv("MGV_DECODE_GROUPS");
   if (ge && atoi(ge) >= 1 && atoi(ge) <= Gpt::MAX_GROUPS) g->groups = atoi(ge);
   const char* e = getenv("MGV_PDL");
@@ -325,11 +348,10 @@ int gpt_destroy(Gpt* g) {
   cudaFree(g->slab);
   cudaFree(g->x); cudaFree(g->ln); cudaFree(g->qkv); cudaFree(g->y); cudaFree(g->h);
   cudaFree(g->dx); cudaFree(g->dqkv32); cudaFree(g->dh32); cudaFree(g->dln); cudaFree(g->dy); cudaFree(g->dh);
-  cudaFree(g->kv); cudaFree(g->dlogits); cudaFree(g->dtokens);
+  cudaFree(g->kv); cudaFree(g->dlogits); cudaFree(g->dtokens); cudaFree(g->stats1); cudaFree(g->stats2);
   if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
   if (g->graph) cudaGraphDestroy(g->graph);
   cudaFree(g->d_state);
-  cudaFree(g->d_prog); cudaFree(g->d_maps); cudaFree(g->d_counters); cudaFree(g->d_trace);
   if (g->stream) cudaStreamDestroy(g->stream);
   if (g->ev_in) cudaEventDestroy(g->ev_in);
   if (g->ev_out) cudaEventDestroy(g->ev_out);
@@ -346,6 +368,7 @@ int gpt_destroy(Gpt* g) {
 // CausalSelfAttention :56-63, GPTClass :207).  src = fp32 device pointer.
 int gpt_load_weight(Gpt* g, const char* name, const float* src, long long numel, cudaStream_t s) {
   MGV_REQUIRE(g && name && src, "gpt_load_weight: null");
+  g->fold_dirty = true;
   const size_t C = g->C;
   auto copy_f32 = [&](float* dst, size_t n, int slot) -> int {
     MGV_REQUIRE(static_cast<size_t>(numel) == n, "gpt_load_weight(%s): numel %lld != expected %zu", name, numel, n);
@@ -476,7 +499,25 @@ int decode_gemm(Gpt* g, const __nv_bfloat16* X, const __nv_bfloat16* W, const fl
 
 // one decode position for the B sequences of one group, rows [b0, b0+B) of the batch (enqueued on s; position
 // read from sa.pos_ptr)
-int enqueue_group_step(Gpt* g, int b0, int B, const SampleArgs& sa, float* att_out, int att_T, cudaStream_t s) {
+// K slice (in 64-wide k-blocks) of a fold GEMM CTA: at most 4 resident k-blocks, at most FOLD_MAX_PARTS slices
+int fold_kbps(int K) {
+  const int nkb = K / 64;
+  int kbps = nkb < 4 ? nkb : 4;
+  while (ceil_div(nkb, kbps) > FOLD_MAX_PARTS) ++kbps;
+  return kbps;
+}
+int fold_kbps_head(int K) {      // one feature tile only: the finest slices give the most CTAs
+  const int nkb = K / 64;
+  int kbps = 1;
+  while (ceil_div(nkb, kbps) > FOLD_MAX_PARTS) ++kbps;
+  return kbps;
+}
+bool fold_eligible(const Gpt* g, int B) {
+  return g->use_fold && B >= 1 && B <= 256 && fold_kbps(4 * g->C) <= 4 && fold_kbps_head(g->C) <= 4;
+}
+
+int enqueue_group_step(Gpt* g, int b0, int B, const SampleArgs& sa, float* att_out, int att_T, cudaStream_t s,
+                       bool first_kernel_pdl) {
   const int C = g->C;
   const DecodeTiles& tl = g->tiles;
   const size_t r0 = static_cast<size_t>(b0);
@@ -489,35 +530,60 @@ int enqueue_group_step(Gpt* g, int b0, int B, const SampleArgs& sa, float* att_o
   __nv_bfloat16* dh = g->dh + r0 * 4 * C;
   const size_t kv_off = r0 * g->nh * g->Tmax * GPT_HEAD_DIM;
   if (att_out) att_out += r0 * g->nh * att_T * att_T;
-  // Experimental fused path (MGV_FUSED_DECODE=1): LayerNorm applied inside the QKV / FC1 / head GEMMs (cluster-wide
-  // row statistics over distributed shared memory) and GELU inside FC2 -> 5 dependent kernels per layer instead of
-  // 8.  Measured SLOWER on B200 (1293 vs 1021 us per position): each fused kernel costs what its two parts cost
-  // (the GELU is recomputed by all 8 feature-tile CTAs, the cluster barrier + DSMEM reads add ~2 us) and
-  // cluster kernels overlap less under programmatic dependent launch.  Kept for the next round's persistent design.
-  static const bool want_fused = getenv("MGV_FUSED_DECODE") != nullptr;
-  const bool fused = want_fused && B <= 64 && (C / 64) % 8 == 0 && (C / 64) / 8 <= 2 && (4 * C / 64) % 16 == 0 &&
-                     (4 * C / 64) / 16 <= 4;
-  if (fused) {
+  if (fold_eligible(g, B)) {
+    // ---- folded chain: 5 kernels per block (see gemm_decode_fold.cu)
+    const int kq = fold_kbps(C), kf2 = fold_kbps(4 * C);
+    const int fbn = (B > 32 && g->fold_bn == 64) ? 64 : 32, fbn2 = (B > 32 && g->fold_bn2 == 64) ? 64 : 32;
+    const int np1 = ceil_div(C / 64, kq);                 // K slices of the GEMMs that consume the residual stream
+    float2* st1 = g->stats1 + r0;
+    float2* st2 = g->stats2 + r0;
+    const int sstride = g->dec_B;
     for (int l = 0; l < g->L; ++l) {
       const GptLayer& w = g->layers[l];
-      MGV_TRY(gemm_decode_ln(w.wqkv, 3 * C, C, dx, B, w.ln1_w, w.ln1_b, w.bqkv, dqkv32, 3 * C, 8, g->pdl, s));
-      MGV_TRY(gpt_attention_decode(dqkv32, B, g->nh, sa.pos_ptr, g->kcache(l) + kv_off, g->vcache(l) + kv_off, g->Tmax,
-                                   dy, (l == g->L - 1) ? att_out : nullptr, att_T, true, dh32,
-                                   static_cast<long long>(B) * 4 * C, s, g->pdl));
+      LnFold f1;
+      f1.stats = st1; f1.nparts = np1; f1.stride = sstride; f1.dim = C; f1.sw = w.sw_qkv; f1.bp = w.bp_qkv;
+      LnFold f2;
+      f2.stats = st2; f2.nparts = np1; f2.stride = sstride; f2.dim = C; f2.sw = w.sw_fc1; f2.bp = w.bp_fc1;
+      // the first kernel of a position must not start before the previous position's sampler has advanced *pos_ptr
+      // (attention reads it ahead of its grid dependency): inside a graph replay positions are serialised anyway
+      const bool pdl0 = g->pdl && (l > 0 || first_kernel_pdl);
+      MGV_TRY(gemm_decode_fold(FOLD_LN, w.wqkv, 3 * C, C, dx, B, w.ln1_w, st1, sstride, nullptr, nullptr, dqkv32, 3 * C, kq,
+                               g->fold_sw, fbn, pdl0, s));
+      MGV_TRY(gpt_attention_decode(dqkv32, B, g->nh, sa.pos_ptr, g->kcache(l) + kv_off, g->vcache(l) + kv_off, g->Tmax, dy,
+                                   (l == g->L - 1) ? att_out : nullptr, att_T, true, dh32,
+                                   static_cast<long long>(B) * 4 * C, s, g->pdl, &f1));
       MGV_TRY(decode_gemm(g, dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, dx, dx, s));
-      MGV_TRY(gemm_decode_ln(w.wfc1, 4 * C, C, dx, B, w.ln2_w, w.ln2_b, w.bfc1, dh32, 4 * C, 8, g->pdl, s));
-      MGV_TRY(gemm_decode_gelu(w.wfc2, C, 4 * C, dh32, B, w.bfc2, dx, C, 16, g->pdl, s));
+      KvPrefetch pf;
+      if (g->kv_prefetch) {     // K / V rows of the layer whose attention runs next (layer 0 of the next position after the last)
+        const int ln = (l + 1) % g->L;
+        pf.k = reinterpret_cast<const char*>(g->kcache(ln) + kv_off);
+        pf.v = reinterpret_cast<const char*>(g->vcache(ln) + kv_off);
+        pf.pos_ptr = sa.pos_ptr;
+        pf.pairs = B * g->nh;
+        pf.row_bytes = GPT_HEAD_DIM * 2;
+        pf.run_stride = static_cast<long long>(g->Tmax) * GPT_HEAD_DIM * 2;
+      }
+      MGV_TRY(gemm_decode_fold(FOLD_LN, w.wfc1, 4 * C, C, dx, B, w.ln2_w, st2, sstride, nullptr, nullptr, dh32, 4 * C, kq,
+                               g->fold_sw, fbn, g->pdl, s, g->kv_prefetch ? &pf : nullptr));
+      MGV_TRY(gemm_decode_fold(FOLD_GELU, w.wfc2, C, 4 * C, dh32, B, nullptr, nullptr, 0, &f2, w.bfc2, dx, C, kf2,
+                               g->fold_sw_gelu, fbn2, g->pdl, s));
       g->launches += 4;
     }
-    MGV_TRY(gemm_decode_ln(g->whead, g->V, C, dx, B, g->lnf_w, g->lnf_b, nullptr, dlogits, g->V, 8, g->pdl, s));
-    MGV_TRY(gpt_sample_step(sa, s, g->pdl));
+    // ln_f + head (minGPT.py:186-188): the same fold; the sampler applies the statistics
+    const int kh = fold_kbps_head(C);
+    MGV_TRY(gemm_decode_fold(FOLD_LN, g->whead, g->V, C, dx, B, g->lnf_w, st1, sstride, nullptr, nullptr, dlogits, g->V, kh,
+                             g->fold_sw, fbn, g->pdl, s));
+    SampleArgs sf = sa;
+    sf.fold.stats = st1; sf.fold.nparts = ceil_div(C / 64, kh); sf.fold.stride = sstride; sf.fold.dim = C;
+    sf.fold.sw = g->sw_head; sf.fold.bp = g->bp_head;
+    MGV_TRY(gpt_sample_step(sf, s, g->pdl));
     g->launches += 2;
     return MGV_OK;
   }
   const bool qs = tl.qkv_split > 1, fs = tl.fc1_split > 1;
   for (int l = 0; l < g->L; ++l) {
     const GptLayer& w = g->layers[l];
-    MGV_TRY(gpt_layernorm(dx, w.ln1_w, w.ln1_b, B, C, dln, nullptr, 0, s, g->pdl));
+    MGV_TRY(gpt_layernorm(dx, w.ln1_w, w.ln1_b, B, C, dln, nullptr, 0, s, g->pdl && (l > 0 || first_kernel_pdl)));
     MGV_TRY(decode_gemm(g, dln, w.wqkv, w.bqkv, B, 3 * C, C, tl.qkv_split, EPI_F32, dqkv32, nullptr, s));
     MGV_TRY(gpt_attention_decode(dqkv32, B, g->nh, sa.pos_ptr, g->kcache(l) + kv_off, g->vcache(l) + kv_off, g->Tmax, dy,
                                  (l == g->L - 1) ? att_out : nullptr, att_T, qs, nullptr, 0, s, g->pdl));
@@ -546,119 +612,17 @@ int enqueue_group_step(Gpt* g, int b0, int B, const SampleArgs& sa, float* att_o
   return MGV_OK;
 }
 
-// ---- stage-program path ------------------------------------------------------------------------------------
-bool program_gemm_shape(int n_feat, int K, int B, int n_ctas, int* ftiles, int* rhalves, int* splits) {
-  if (K % 64 != 0) return false;
-  const int nkb = K / 64;
-  *ftiles = (n_feat + 63) / 64;
-  *rhalves = (B + 31) / 32;
-  *splits = (nkb + DP_MAX_KB - 1) / DP_MAX_KB;
-  return *ftiles * *rhalves * *splits <= n_ctas;
-}
-
-bool program_eligible(const Gpt* g, int B) {
-  if (!g->use_program || B < 1 || B > 64 || g->C > 1024 || g->C % 64 != 0) return false;
-  const int n = num_sms();
-  int t, r, sp;
-  return program_gemm_shape(3 * g->C, g->C, B, n, &t, &r, &sp) && program_gemm_shape(g->C, g->C, B, n, &t, &r, &sp) &&
-         program_gemm_shape(4 * g->C, g->C, B, n, &t, &r, &sp) && program_gemm_shape(g->C, 4 * g->C, B, n, &t, &r, &sp) &&
-         program_gemm_shape(g->V, g->C, B, n, &t, &r, &sp);
-}
-
-// builds (or reuses) the device-side stage list and tensor-map table for batch B; not capturable (synchronous copies)
-int build_decode_program(Gpt* g, int B, cudaStream_t s) {
-  if (g->prog_B == B && g->d_prog) return MGV_OK;
-  const int C = g->C, L = g->L, n_ctas = num_sms();
-  std::vector<CUtensorMap> maps(3 + 4 * L + 1);
-  // activations: box = 64 k x 32 sequences; weights: box = 64 k x 64 rows
-  MGV_TRY(make_tmap_2d_bf16(&maps[0], g->dln, C, B, static_cast<uint64_t>(C) * 2, 64, 32));
-  MGV_TRY(make_tmap_2d_bf16(&maps[1], g->dy, C, B, static_cast<uint64_t>(C) * 2, 64, 32));
-  MGV_TRY(make_tmap_2d_bf16(&maps[2], g->dh, 4 * C, B, static_cast<uint64_t>(4 * C) * 2, 64, 32));
-  for (int l = 0; l < L; ++l) {
+// fold vectors of every GEMM that consumes a LayerNorm (recomputed after any weight load)
+int prepare_fold(Gpt* g, cudaStream_t s) {
+  if (!g->use_fold || !g->fold_dirty) return MGV_OK;
+  const int C = g->C;
+  for (int l = 0; l < g->L; ++l) {
     const GptLayer& w = g->layers[l];
-    MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * l + 0], w.wqkv, C, 3 * C, static_cast<uint64_t>(C) * 2, 64, 64));
-    MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * l + 1], w.wproj, C, C, static_cast<uint64_t>(C) * 2, 64, 64));
-    MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * l + 2], w.wfc1, C, 4 * C, static_cast<uint64_t>(C) * 2, 64, 64));
-    MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * l + 3], w.wfc2, 4 * C, C, static_cast<uint64_t>(4 * C) * 2, 64, 64));
+    MGV_TRY(gpt_fold_prepare(w.wqkv, 3 * C, C, w.ln1_w, w.ln1_b, w.bqkv, w.sw_qkv, w.bp_qkv, s));
+    MGV_TRY(gpt_fold_prepare(w.wfc1, 4 * C, C, w.ln2_w, w.ln2_b, w.bfc1, w.sw_fc1, w.bp_fc1, s));
   }
-  MGV_TRY(make_tmap_2d_bf16(&maps[3 + 4 * L], g->whead, C, g->V, static_cast<uint64_t>(C) * 2, 64, 64));
-
-  std::vector<DecStage> prog;
-  g->prog_ranges.clear();
-  auto ln = [&](const float* gamma, const float* beta) {
-    DecStage d;
-    memset(&d, 0, sizeof(d));
-    d.type = DST_LN; d.B = B; d.C = C;
-    d.x = g->dx; d.gamma = gamma; d.beta = beta; d.ln_out = g->dln;
-    prog.push_back(d);
-  };
-  auto gemm = [&](int map_w, int map_x, int n_feat, int K, int mode, const float* bias, void* out, long long ldo) -> int {
-    DecStage d;
-    memset(&d, 0, sizeof(d));
-    d.type = DST_GEMM; d.B = B; d.C = C;
-    d.map_w = map_w; d.map_x = map_x; d.n_feat = n_feat; d.nkb = K / 64;
-    MGV_REQUIRE(program_gemm_shape(n_feat, K, B, n_ctas, &d.ftiles, &d.rhalves, &d.splits),
-                "decode program: GEMM %dx%d does not fit", n_feat, K);
-    d.mode = (mode == DGM_ADD_F32 && d.splits > 1) ? DGM_RED_F32 : mode;
-    MGV_REQUIRE(d.splits == 1 || d.mode == DGM_RED_F32, "decode program: split-K GEMM %dx%d needs the reduction epilogue", n_feat, K);
-    d.bias = bias; d.out = out; d.ldo = ldo;
-    prog.push_back(d);
-    return MGV_OK;
-  };
-  // kernel 0: LN1 + QKV of block 0
-  ln(g->layers[0].ln1_w, g->layers[0].ln1_b);
-  MGV_TRY(gemm(3 + 0, 0, 3 * C, C, DGM_STORE_F32, g->layers[0].bqkv, g->dqkv32, 3 * C));
-  g->prog_ranges.push_back({0, 2});
-  for (int l = 0; l < L; ++l) {
-    const GptLayer& w = g->layers[l];
-    const int begin = static_cast<int>(prog.size());
-    MGV_TRY(gemm(3 + 4 * l + 1, 1, C, C, DGM_ADD_F32, w.bproj, g->dx, C));                 // x += proj(y)
-    ln(w.ln2_w, w.ln2_b);
-    MGV_TRY(gemm(3 + 4 * l + 2, 0, 4 * C, C, DGM_GELU_BF16, w.bfc1, g->dh, 4 * C));        // h = gelu(fc1(ln2(x)))
-    MGV_TRY(gemm(3 + 4 * l + 3, 2, C, 4 * C, DGM_ADD_F32, w.bfc2, g->dx, C));              // x += fc2(h)
-    if (l + 1 < L) {
-      const GptLayer& nx = g->layers[l + 1];
-      ln(nx.ln1_w, nx.ln1_b);
-      MGV_TRY(gemm(3 + 4 * (l + 1) + 0, 0, 3 * C, C, DGM_STORE_F32, nx.bqkv, g->dqkv32, 3 * C));
-    } else {
-      ln(g->lnf_w, g->lnf_b);
-      MGV_TRY(gemm(3 + 4 * L, 0, g->V, C, DGM_STORE_F32, nullptr, g->dlogits, g->V));
-    }
-    g->prog_ranges.push_back({begin, static_cast<int>(prog.size())});
-  }
-  cudaFree(g->d_prog); cudaFree(g->d_maps);
-  g->d_prog = nullptr; g->d_maps = nullptr;
-  g->prog_B = 0;
-  MGV_CHECK_CUDA(cudaMalloc(&g->d_prog, prog.size() * sizeof(DecStage)));
-  MGV_CHECK_CUDA(cudaMalloc(&g->d_maps, maps.size() * sizeof(CUtensorMap)));
-  if (!g->d_counters) MGV_CHECK_CUDA(cudaMalloc(&g->d_counters, 256 * sizeof(unsigned int)));
-  if (!g->d_trace && getenv("MGV_DP_TRACE")) {
-    MGV_CHECK_CUDA(cudaMalloc(&g->d_trace, 256 * DP_TRACE_WORDS * 8));
-    MGV_CHECK_CUDA(cudaMemset(g->d_trace, 0, 256 * DP_TRACE_WORDS * 8));
-  }
-  MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_prog, prog.data(), prog.size() * sizeof(DecStage), cudaMemcpyHostToDevice, s));
-  MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s));
-  MGV_CHECK_CUDA(cudaStreamSynchronize(s));
-  g->prog_B = B;
-  return MGV_OK;
-}
-
-// one decode position through the stage program: L+1 persistent kernels interleaved with the L attention kernels
-int enqueue_program_step(Gpt* g, int B, const SampleArgs& sa, float* att_out, int att_T, cudaStream_t s) {
-  const int L = g->L, n_ctas = num_sms();
-  MGV_REQUIRE(g->prog_B == B && static_cast<int>(g->prog_ranges.size()) == L + 1 && L + 1 <= 256, "decode program not built");
-  MGV_CHECK_CUDA(cudaMemsetAsync(g->d_counters, 0, (L + 1) * sizeof(unsigned int), s));
-  MGV_TRY(decode_program_launch(g->d_prog, g->prog_ranges[0].first, g->prog_ranges[0].second, g->d_maps, g->d_counters,
-                                n_ctas, g->pdl, s, g->d_trace));
-  for (int l = 0; l < L; ++l) {
-    MGV_TRY(gpt_attention_decode(g->dqkv32, B, g->nh, sa.pos_ptr, g->kcache(l), g->vcache(l), g->Tmax, g->dy,
-                                 (l == L - 1) ? att_out : nullptr, att_T, false, nullptr, 0, s, g->pdl));
-    MGV_TRY(decode_program_launch(g->d_prog, g->prog_ranges[l + 1].first, g->prog_ranges[l + 1].second, g->d_maps,
-                                  g->d_counters + l + 1, n_ctas, g->pdl, s,
-                                  g->d_trace ? g->d_trace + (l + 1) * DP_TRACE_WORDS : nullptr));
-  }
-  MGV_TRY(gpt_sample_step(sa, s, g->pdl));
-  g->launches += 2 * L + 2;
+  MGV_TRY(gpt_fold_prepare(g->whead, g->Vout, C, g->lnf_w, g->lnf_b, nullptr, g->sw_head, g->bp_head, s));
+  g->fold_dirty = false;
   return MGV_OK;
 }
 
@@ -670,9 +634,9 @@ int decode_groups(const Gpt* g, int B) {
 
 // one decode position for all B sequences: the sequence groups fork from s, run their chains on their own
 // streams and join back (inside a stream capture this becomes parallel branches of the step graph)
-int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa0, float* att_out, int att_T, cudaStream_t s) {
+int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa0, float* att_out, int att_T, cudaStream_t s,
+                        bool first_kernel_pdl) {
   const int ng = decode_groups(g, B);
-  if (ng == 1 && g->prog_B == B && program_eligible(g, B)) return enqueue_program_step(g, B, sa0, att_out, att_T, s);
   if (ng > 1) MGV_CHECK_CUDA(cudaEventRecord(g->ev_fork, s));
   int b0 = 0;
   for (int c = 0; c < ng; ++c) {
@@ -687,7 +651,7 @@ int enqueue_decode_step(Gpt* g, int B, const SampleArgs& sa0, float* att_out, in
     sa.x_next = sa0.x_next + static_cast<size_t>(b0) * g->C;
     sa.pos_ptr = g->d_state + 8 + 2 * c;
     sa.done_counter = reinterpret_cast<unsigned int*>(g->d_state + 9 + 2 * c);
-    const int rc = enqueue_group_step(g, b0, Bc, sa, att_out, att_T, cs);
+    const int rc = enqueue_group_step(g, b0, Bc, sa, att_out, att_T, cs, first_kernel_pdl);
     if (rc != MGV_OK) return rc;
     if (c > 0) MGV_CHECK_CUDA(cudaEventRecord(g->ev_join[c], cs));
     b0 += Bc;
@@ -760,8 +724,7 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state + 8, init_state, sizeof(init_state), cudaMemcpyHostToDevice, s));
   MGV_CHECK_CUDA(cudaMemcpyAsync(g->d_state + 4, &seed, sizeof(seed), cudaMemcpyHostToDevice, s));
 
-  SampleArgs sa;
-  memset(&sa, 0, sizeof(sa));
+  SampleArgs sa{};
   sa.logits_acc = g->dlogits;
   sa.B = B; sa.C = g->C; sa.V = g->V;
   sa.temperature = temperature; sa.top_k = top_k; sa.do_sample = do_sample;
@@ -772,8 +735,7 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   sa.x_next = g->dx; sa.logits_out = nullptr;
   sa.done_counter = reinterpret_cast<unsigned int*>(g->d_state + 9);
 
-  if (decode_groups(g, B) == 1 && program_eligible(g, B)) MGV_TRY(build_decode_program(g, B, s));
-  else g->prog_B = 0;
+  MGV_TRY(prepare_fold(g, s));
   cudaGraph_t tmp_graph = nullptr;
   cudaGraphExec_t tmp_exec = nullptr;
   if (use_graph) {
@@ -790,7 +752,7 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
       cudaGraph_t graph = nullptr;
       MGV_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       const long long before = g->launches;
-      const int rc = enqueue_decode_step(g, B, sa, att_out, Tf, s);
+      const int rc = enqueue_decode_step(g, B, sa, att_out, Tf, s, true);
       per_step = g->launches - before;
       g->launches = before;
       const cudaError_t ce = cudaStreamEndCapture(s, &graph);
@@ -821,7 +783,7 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
     }
     g->launches += per_step * steps;
   } else {
-    for (int k = 0; k < steps; ++k) MGV_TRY(enqueue_decode_step(g, B, sa, att_out, Tf, s));
+    for (int k = 0; k < steps; ++k) MGV_TRY(enqueue_decode_step(g, B, sa, att_out, Tf, s, false));
   }
   // generated tokens: internal buffer columns [t0, t0+steps) -> x_out
   const cudaError_t e0 = cudaMemcpy2DAsync(x_out + t0, static_cast<size_t>(ld) * 8, g->dtokens + t0, static_cast<size_t>(tld) * 8,
@@ -829,18 +791,6 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   const cudaError_t e1 = cudaEventRecord(g->ev_out, s);
   const cudaError_t e2 = cudaStreamWaitEvent(caller, g->ev_out, 0);
   const int rc = read_err_flag(g, s, "gpt_generate");  // synchronises s
-  if (g->d_trace && g->prog_B == B) {   // diagnostics: stage timeline of the last position (CTA 0)
-    std::vector<unsigned long long> tr(static_cast<size_t>(g->L + 1) * DP_TRACE_WORDS);
-    if (cudaMemcpy(tr.data(), g->d_trace, tr.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
-      const unsigned long long t0 = tr[0];
-      for (int k = 0; k <= g->L && k < 4; ++k) {
-        fprintf(stderr, "[dp-trace] kernel %d:", k);
-        for (int i = 0; i < DP_TRACE_WORDS; ++i)
-          fprintf(stderr, " %.2f", tr[k * DP_TRACE_WORDS + i] ? (static_cast<double>(tr[k * DP_TRACE_WORDS + i]) - static_cast<double>(t0)) * 1e-3 : 0.0);
-        fprintf(stderr, "\n");
-      }
-    }
-  }
   if (tmp_exec) cudaGraphExecDestroy(tmp_exec);
   if (tmp_graph) cudaGraphDestroy(tmp_graph);
   MGV_CHECK_CUDA(e0);

@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(AD_THREADS, 7)
 attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ pos_ptr,
                    __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache, int Tmax,
                    __nv_bfloat16* __restrict__ y, float* __restrict__ att_rows, int Tatt, int zero_consumed,
-                   float* __restrict__ zero_buf, int zero_per_cta) {
+                   float* __restrict__ zero_buf, int zero_per_cta, const LnFold fold) {
   pdl_launch_dependents();
   __shared__ __align__(16) float sq[GPT_HEAD_DIM];
   __shared__ __align__(16) __nv_bfloat16 sk[GPT_HEAD_DIM];
@@ -412,6 +412,16 @@ attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ po
   // ---- first pass of K rows: positions < pos were written by earlier steps, so load before the dependency
   uint4 b0[AD_KPP], b1[AD_KPP];
   load_rows(kc, nullptr, 0, b0);
+  // folded LayerNorm (gemm_decode_fold.cu): q, k, v arrive as raw accumulators of W (gamma.x); the fold vectors are
+  // weights-like constants, so they are also fetched before the dependency resolves
+  float f_sw[3] = {0.f, 0.f, 0.f}, f_bp[3] = {0.f, 0.f, 0.f};
+  if (fold.stats != nullptr && t < GPT_HEAD_DIM) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      f_sw[i] = __ldg(fold.sw + i * C + h * GPT_HEAD_DIM + t);
+      f_bp[i] = __ldg(fold.bp + i * C + h * GPT_HEAD_DIM + t);
+    }
+  }
   pdl_wait();
   // clear this CTA's slice of the FC1 split-K accumulator: its last reader (the previous layer's FC2) has
   // completed and the next writer (this layer's FC1) runs after this kernel
@@ -419,10 +429,25 @@ attn_decode_kernel(float* __restrict__ qkv32, int nh, const int* __restrict__ po
     for (int i = t; i < zero_per_cta; i += AD_THREADS) zero_buf[static_cast<long long>(blockIdx.x) * zero_per_cta + i] = 0.f;
   if (t < GPT_HEAD_DIM) {
     float* base = qkv32 + static_cast<long long>(b) * 3 * C + h * GPT_HEAD_DIM + t;
+    float qf = __ldcg(base), kf = __ldcg(base + C), vf = __ldcg(base + 2 * C);
+    if (fold.stats != nullptr) {
+      float s = 0.f, ss = 0.f;
+      for (int z = 0; z < fold.nparts; ++z) {     // fixed order: deterministic
+        const float2 p = __ldcg(fold.stats + static_cast<long long>(z) * fold.stride + b);
+        s += p.x;
+        ss += p.y;
+      }
+      const float inv_n = 1.0f / static_cast<float>(fold.dim);
+      const float mean = s * inv_n;
+      const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + 1e-5f);
+      qf = fmaf(rstd, fmaf(-mean, f_sw[0], qf), f_bp[0]);
+      kf = fmaf(rstd, fmaf(-mean, f_sw[1], kf), f_bp[1]);
+      vf = fmaf(rstd, fmaf(-mean, f_sw[2], vf), f_bp[2]);
+    }
     // q is rounded to bf16 like the prefill path (which stores q,k,v as bf16)
-    sq[t] = __bfloat162float(__float2bfloat16(base[0]));
-    const __nv_bfloat16 kb = __float2bfloat16(base[C]);
-    const __nv_bfloat16 vb = __float2bfloat16(base[2 * C]);
+    sq[t] = __bfloat162float(__float2bfloat16(qf));
+    const __nv_bfloat16 kb = __float2bfloat16(kf);
+    const __nv_bfloat16 vb = __float2bfloat16(vf);
     if (zero_consumed) {  // the next layer's split-K QKV GEMM accumulates into this buffer with atomics
       base[0] = 0.f;
       base[C] = 0.f;
@@ -614,8 +639,22 @@ sample_step_kernel(const SampleArgs a) {
 
   // ---- logits / temperature (minGPT.py:346); the accumulator is cleared for the next position's split-K head GEMM
   float* lrow = a.logits_acc + static_cast<long long>(b) * a.V;
+  float f_mean = 0.f, f_rstd = 1.f;
+  if (a.fold.stats != nullptr) {    // folded ln_f: raw accumulator of W_head (gamma.x) -> logits (gemm_decode_fold.cu)
+    float s = 0.f, ss = 0.f;
+    for (int z = 0; z < a.fold.nparts; ++z) {
+      const float2 p = __ldcg(a.fold.stats + static_cast<long long>(z) * a.fold.stride + b);
+      s += p.x;
+      ss += p.y;
+    }
+    const float inv_n = 1.0f / static_cast<float>(a.fold.dim);
+    f_mean = s * inv_n;
+    f_rstd = rsqrtf(fmaxf(ss * inv_n - f_mean * f_mean, 0.f) + 1e-5f);
+  }
   for (int i = t; i < a.V; i += SAMPLE_THREADS) {
-    const float l = __fdiv_rn(lrow[i], a.temperature);
+    float raw = __ldcg(lrow + i);
+    if (a.fold.stats != nullptr) raw = fmaf(f_rstd, fmaf(-f_mean, __ldg(a.fold.sw + i), raw), __ldg(a.fold.bp + i));
+    const float l = __fdiv_rn(raw, a.temperature);
     lrow[i] = 0.f;
     sl[i] = l;
     if (a.logits_out) a.logits_out[static_cast<long long>(b) * a.V + i] = l;
@@ -836,15 +875,16 @@ int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_
 
 int gpt_attention_decode(float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
                          __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, bool zero_consumed,
-                         float* zero_buf, long long zero_count, cudaStream_t s, bool pdl) {
+                         float* zero_buf, long long zero_count, cudaStream_t s, bool pdl, const LnFold* fold) {
   MGV_REQUIRE(zero_buf == nullptr || (B > 0 && zero_count % (static_cast<long long>(B) * nh) == 0),
               "attention: zero_count must be a multiple of the CTA count");
   MGV_REQUIRE(Tmax <= GPT_MAX_T, "attention: Tmax=%d exceeds %d", Tmax, GPT_MAX_T);
   if (B == 0) return MGV_OK;
   LaunchCfg lc(dim3(B * nh), dim3(AD_THREADS), 0, s, pdl);
   const int zero_per_cta = zero_buf ? static_cast<int>(zero_count / (static_cast<long long>(B) * nh)) : 0;
+  const LnFold f = fold ? *fold : LnFold();
   MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_kernel, qkv32, nh, pos_ptr, kcache, vcache, Tmax, y, att_rows,
-                                    Tatt, zero_consumed ? 1 : 0, zero_buf, zero_per_cta));
+                                    Tatt, zero_consumed ? 1 : 0, zero_buf, zero_per_cta, f));
   return MGV_OK;
 }
 

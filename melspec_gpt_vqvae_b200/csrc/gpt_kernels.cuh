@@ -29,10 +29,11 @@ int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_
 // One decode position: q,k,v fp32 [B, 3C] for position *pos_ptr; appends k,v to the cache and
 // attends over positions 0..pos.  att_rows (optional): fp32 [B, nh, Tatt, Tatt] pre-zeroed; entries 0..pos of row pos are written.
 // zero_consumed: the q,k,v accumulators are cleared after they are read (ready for the next split-K reduction).
-// zero_buf / zero_count: optional second fp32 buffer cleared cooperatively (the FC1 accumulator in the fused decode path).
+// zero_buf / zero_count: optional second fp32 buffer cleared cooperatively (the FC1 split-K accumulator).
+// fold: q, k, v are raw accumulators of a FOLD_LN GEMM (gemm_decode_fold.cu); the LayerNorm is applied here.
 int gpt_attention_decode(float* qkv32, int B, int nh, const int* pos_ptr, __nv_bfloat16* kcache,
                          __nv_bfloat16* vcache, int Tmax, __nv_bfloat16* y, float* att_rows, int Tatt, bool zero_consumed,
-                         float* zero_buf, long long zero_count, cudaStream_t s, bool pdl);
+                         float* zero_buf, long long zero_count, cudaStream_t s, bool pdl, const LnFold* fold = nullptr);
 
 // h = gelu_erf(h32) as bf16 (split-K FC1 path)
 int gpt_gelu_bf16(float* h32, long long n, __nv_bfloat16* out, bool zero_consumed, cudaStream_t s, bool pdl);
@@ -55,6 +56,7 @@ struct SampleArgs {
   float* x_next;           // [B, C]: embedding of the sampled token at position pos+1
   float* logits_out;       // optional [B, V]: logits of this step (after temperature, before top-k)
   unsigned int* done_counter;  // device scratch (zero-initialised) used to advance *pos_ptr once per step
+  LnFold fold;             // folded ln_f (stats == nullptr: logits_acc already holds the logits)
 };
 int gpt_sample_step(const SampleArgs& a, cudaStream_t s, bool pdl);
 

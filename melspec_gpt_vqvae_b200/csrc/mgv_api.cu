@@ -263,13 +263,36 @@ int mgv_test_gemm_swapab(int impl, const void* W, const void* X, int M, int N, i
   MGV_API_END
 }
 
-int mgv_test_gemm_fused(int mode, const void* W, const float* src, int Nw, int B, int K, const float* gamma,
-                        const float* beta, const float* bias, float* out, int split_k, mgv_stream_t stream) {
+int mgv_test_gemm_fold(int mode, const void* W, const float* src, int Nw, int B, int K, const float* gamma_or_sw,
+                       const float* beta_or_bp, const float* bias, const float* stats_in, int nparts, int ln_dim,
+                       float* out, int kbps, int staging_warps, mgv_stream_t stream) {
   MGV_API_BEGIN
   MGV_TRY(check_device());
-  if (mode == 0)
-    return gemm_decode_gelu(W, Nw, K, src, B, bias, out, Nw, split_k, false, static_cast<cudaStream_t>(stream));
-  return gemm_decode_ln(W, Nw, K, src, B, gamma, beta, bias, out, Nw, split_k, false, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (mode == FOLD_GELU) {
+    LnFold in;
+    in.stats = reinterpret_cast<const float2*>(stats_in); in.nparts = nparts; in.stride = B; in.dim = ln_dim;
+    in.sw = gamma_or_sw; in.bp = beta_or_bp;
+    return gemm_decode_fold(FOLD_GELU, W, Nw, K, src, B, nullptr, nullptr, 0, &in, bias, out, Nw, kbps, staging_warps % 100, staging_warps >= 100 ? 64 : 32, false, s);
+  }
+  // FOLD_LN: raw accumulation + statistics, then the consumer-side correction (what attention / FC2 / the sampler do)
+  const int parts = ceil_div(K / 64, kbps);
+  float *sw = nullptr, *bp = nullptr;
+  float2* stats = nullptr;
+  MGV_CHECK_CUDA(cudaMalloc(&sw, static_cast<size_t>(Nw) * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&bp, static_cast<size_t>(Nw) * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&stats, static_cast<size_t>(parts) * B * sizeof(float2)));
+  int rc = gpt_fold_prepare(W, Nw, K, gamma_or_sw, beta_or_bp, bias, sw, bp, s);
+  if (rc == MGV_OK)
+    rc = gemm_decode_fold(FOLD_LN, W, Nw, K, src, B, gamma_or_sw, stats, B, nullptr, nullptr, out, Nw, kbps, staging_warps % 100, staging_warps >= 100 ? 64 : 32, false, s);
+  if (rc == MGV_OK) {
+    LnFold f;
+    f.stats = stats; f.nparts = parts; f.stride = B; f.dim = K; f.sw = sw; f.bp = bp;
+    rc = gpt_fold_apply(out, B, Nw, f, s);
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(sw); cudaFree(bp); cudaFree(stats);
+  return rc;
   MGV_API_END
 }
 

@@ -71,6 +71,17 @@ struct LaunchCfg {
   }
 };
 
+// Statistics + fold vectors of a FOLD_LN GEMM, handed to whoever reads its raw accumulator:
+//   value[f] = rstd * (acc[f] - mu * sw[f]) + bp[f],   mu / rstd from sum_z stats[z * stride + row] over `dim` elements.
+struct LnFold {
+  const float2* stats = nullptr;   // [nparts][stride] per-K-slice partial (sum, sum of squares) of the LayerNorm input rows
+  int nparts = 0;
+  int stride = 0;
+  int dim = 0;                     // row length of the LayerNorm (n_embd)
+  const float* sw = nullptr;       // [features] W gamma
+  const float* bp = nullptr;       // [features] W beta + bias
+};
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 
@@ -109,6 +120,23 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 // exact (erf) GELU as torch.nn.GELU() default (reference: transformer/minGPT.py:102)
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+// The same GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 plus the approx-unit error of rcp / ex2,
+// ~1e-6, before the caller rounds to bf16 whose half-ulp is 2e-3 relative): 16 branch-free instructions, two of them
+// on the special-function unit, instead of erff's two divergent polynomial paths.  Used where the activation is
+// recomputed by several CTAs (gemm_decode_fold.cu).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);      // 0.5 x (1 + sign(x) erf|z|)
 }
 // x * sigmoid(x); fast division (rcp.approx + mul): the result is rounded to bf16 by every caller that stores it
 __device__ __forceinline__ float swish(float x) { return __fdividef(x, 1.0f + __expf(-x)); }

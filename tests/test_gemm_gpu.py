@@ -79,27 +79,55 @@ def test_gemm_swapab_vs_torch(M, N, K, bn, split, epi):
     assert (out.float() - ref).abs().max().item() <= tol
 
 
-@pytest.mark.parametrize("mode,Nw,B,K,split", [
-    (0, 1024, 64, 4096, 16), (0, 1024, 5, 4096, 16), (0, 128, 64, 256, 1),
-    (1, 3072, 64, 1024, 8), (1, 4096, 64, 1024, 8), (1, 128, 64, 1024, 8), (1, 3072, 3, 1024, 8), (1, 256, 64, 128, 1),
+@pytest.mark.parametrize("Nw,B,K,kbps,sw", [
+    (3072, 64, 1024, 4, 4), (4096, 64, 1024, 4, 8), (128, 64, 1024, 1, 4), (3072, 3, 1024, 4, 4), (256, 64, 128, 2, 4),
+    (576, 37, 192, 3, 8), (1024, 130, 1024, 2, 4), (3072, 64, 1024, 4, 108), (1024, 130, 1024, 4, 108), (576, 37, 192, 3, 108),
 ])
-def test_fused_decode_gemm(mode, Nw, B, K, split):
-    """decode GEMMs with the activation operand produced in-kernel: GELU(fp32 src) or LayerNorm(fp32 x) (cluster stats)."""
-    torch.manual_seed(Nw + B + K + mode)
+def test_fold_ln_decode_gemm(Nw, B, K, kbps, sw):
+    """FOLD_LN: W LN(x) computed as rstd * (W bf16(gamma x) - mu W gamma) + W beta + b (decode chain, gemm_decode_fold.cu)
+    against LayerNorm + matmul in fp32 (reference: Block.forward transformer/minGPT.py:107-119).  The rows carry a
+    non-zero mean so that the mean-cancellation term is exercised."""
+    torch.manual_seed(Nw + B + K)
     W = (torch.randn(Nw, K, device="cuda") * 0.05).bfloat16()
-    src = torch.randn(B, K, device="cuda") * (1.0 if mode == 0 else 2.0) + (0.0 if mode == 0 else 0.3)
+    src = torch.randn(B, K, device="cuda") * 2.0 + 0.3
     gamma = 1 + 0.1 * torch.randn(K, device="cuda")
     beta = 0.1 * torch.randn(K, device="cuda")
     bias = torch.randn(Nw, device="cuda")
+    out = torch.zeros(B, Nw, device="cuda")
+    ref = torch.nn.functional.layer_norm(src, (K,), gamma, beta, 1e-5) @ W.float().t() + bias
+    _lib.check(_lib.load().mgv_test_gemm_fold(0, _lib.ptr(W), _lib.ptr(src), Nw, B, K, _lib.ptr(gamma), _lib.ptr(beta),
+                                              _lib.ptr(bias), None, 0, 0, _lib.ptr(out), kbps, sw, S0))
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    err = (out - ref).abs().max().item()
+    assert err <= 4e-3 * scale, "max err %.3e (scale %.3e)" % (err, scale)
+
+
+@pytest.mark.parametrize("Nw,B,K,kbps,sw,nparts", [
+    (1024, 64, 4096, 4, 8, 4), (1024, 64, 4096, 4, 4, 4), (1024, 5, 4096, 4, 8, 16), (128, 64, 256, 4, 8, 1),
+    (192, 37, 768, 3, 4, 4), (1024, 64, 4096, 4, 108, 4), (192, 37, 768, 3, 108, 4), (1024, 130, 4096, 4, 108, 4),
+])
+def test_fold_gelu_decode_gemm(Nw, B, K, kbps, sw, nparts):
+    """FOLD_GELU: FC2 applies the producer's folded LayerNorm, the bias and the erf GELU while it stages its operand
+    (reference: mlp transformer/minGPT.py:100-105)."""
+    torch.manual_seed(Nw + B + K + nparts)
+    dim = 1024
+    W = (torch.randn(Nw, K, device="cuda") * 0.05).bfloat16()
+    src = torch.randn(B, K, device="cuda") * 3.0
+    swv = torch.randn(K, device="cuda")
+    bpv = 0.2 * torch.randn(K, device="cuda")
+    bias = torch.randn(Nw, device="cuda")
+    x = torch.randn(B, dim, device="cuda") * 1.5 + 0.4            # the LayerNorm input whose statistics travel
+    parts = x.view(B, nparts, dim // nparts)
+    stats = torch.stack([parts.sum(-1), (parts * parts).sum(-1)], dim=-1).permute(1, 0, 2).contiguous()   # (nparts, B, 2)
+    mu = x.mean(-1, keepdim=True)
+    rstd = torch.rsqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5)
+    act = torch.nn.functional.gelu(rstd * (src - mu * swv) + bpv)
     init = torch.randn(B, Nw, device="cuda")
     out = init.clone()
-    if mode == 0:
-        act = torch.nn.functional.gelu(src)
-    else:
-        act = torch.nn.functional.layer_norm(src, (K,), gamma, beta, 1e-5)
     ref = init + act.bfloat16().float() @ W.float().t() + bias
-    _lib.check(_lib.load().mgv_test_gemm_fused(mode, _lib.ptr(W), _lib.ptr(src), Nw, B, K, _lib.ptr(gamma), _lib.ptr(beta),
-                                               _lib.ptr(bias), _lib.ptr(out), split, S0))
+    _lib.check(_lib.load().mgv_test_gemm_fold(1, _lib.ptr(W), _lib.ptr(src), Nw, B, K, _lib.ptr(swv), _lib.ptr(bpv),
+                                              _lib.ptr(bias), _lib.ptr(stats), nparts, dim, _lib.ptr(out), kbps, sw, S0))
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
     err = (out - ref).abs().max().item()

@@ -93,8 +93,8 @@ def _lit(cfg, sd):
 
 # the decode loop has three schedules: the default PDL kernel chain, two concurrent sequence
 # groups, and the persistent stage-program kernels; the environment is read when the handle is created
-@pytest.mark.parametrize("decode_env", [{}, {"MGV_DECODE_GROUPS": "2"}, {"MGV_DECODE_PROGRAM": "1"}],
-                         ids=["pdl_chain", "two_groups", "stage_program"])
+@pytest.mark.parametrize("decode_env", [{}, {"MGV_DECODE_GROUPS": "2"}, {"MGV_DECODE_FOLD": "0"}],
+                         ids=["fold_chain", "two_groups", "separate_layernorm_chain"])
 def test_greedy_sample_vs_golden_and_kv_cache_consistency(decode_env, monkeypatch):
     for k, v in decode_env.items():
         monkeypatch.setenv(k, v)

@@ -52,6 +52,13 @@ for e in ev:
         cur_e = max(cur_e, b)
 busy += cur_e - cur_s
 print("union of kernel intervals %.0f us of span %.0f us ; sum of durations %.0f us" % (busy, tot, sum(sum(v) for v in dur.values())))
+# stage cost = time from the previous kernel's END to this kernel's END (the chain is serial), averaged per kernel
+stage = collections.defaultdict(list)
+for i in range(1, len(ev)):
+    stage[kname(ev[i]).split(" stream=")[0]].append(ev[i]["ts"] + ev[i]["dur"] - (ev[i - 1]["ts"] + ev[i - 1]["dur"]))
+print("stage cost (end-to-end delta to the previous kernel), average us and share of the span:")
+for k, v in stage.items():
+    print("  %-42s n=%5d avg %6.2f us  sum %8.0f us  %5.1f %%" % (k, len(v), sum(v) / len(v), sum(v), 100.0 * sum(v) / tot))
 # one layer of the last position in detail
 last = ev[-60:-30]
 t0 = last[0]["ts"]
