@@ -129,6 +129,11 @@ int mgv_gpt_cross_entropy(mgv_gpt_t* g, const float* logits, const int64_t* targ
 /* number of kernels libmgv launched in the last forward / generate call on this handle */
 int64_t mgv_gpt_last_launches(const mgv_gpt_t* g);
 
+/* One-shot inspection hook for parity tests: the NEXT mgv_gpt_generate call on this handle also writes the logits of
+ * every decode step (after the temperature division, before top-k; reference transformer/minGPT.py:346) to
+ * buf (steps, B, V) fp32, device memory owned by the caller.  NULL cancels a pending request. */
+int mgv_gpt_set_step_logits(mgv_gpt_t* g, float* buf);
+
 /* ------------------------------------------------------------------ (3) VQVAE -------- */
 
 typedef struct mgv_vqvae mgv_vqvae_t;

@@ -34,6 +34,7 @@ SIGNATURES = {
     "mgv_gpt_generate": (I, [VP, VP, I, I, VP, VP, I, I, F, I, I, ctypes.c_uint64, VP, VP, I, VP]),
     "mgv_gpt_cross_entropy": (I, [VP, VP, VP, I64, I, VP, VP]),
     "mgv_gpt_last_launches": (I64, [VP]),
+    "mgv_gpt_set_step_logits": (I, [VP, VP]),
     "mgv_vqvae_create": (I, [I, I, ctypes.POINTER(VP)]),
     "mgv_vqvae_destroy": (I, [VP]),
     "mgv_vqvae_load_weight": (I, [VP, ctypes.c_char_p, VP, I64, VP]),

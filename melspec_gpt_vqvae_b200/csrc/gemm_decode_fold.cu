@@ -41,8 +41,6 @@ struct FoldParams {
   const float* bias;         // [Nw] added by split 0 (or null)
   float* out;                // fp32 [B, ldo], accumulated with red.add
   long long ldo;
-  KvPrefetch pf;             // optional L2 prefetch of the next layer's KV cache rows
-  int exact_erf;             // FOLD_GELU: erff instead of the A&S 7.1.26 form (MGV_FOLD_EXACT_ERF=1)
 };
 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
@@ -95,20 +93,6 @@ gemm_decode_fold_kernel(const __grid_constant__ CUtensorMap tmW, const FoldParam
       mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(nkb) * FA_BYTES);
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + kb * FSTAGE, &tmW, w_bar, (kb0 + kb) * FBK, m0, kEvictFirst);
     }
-    // This warp is idle from here on: it pulls its share of the NEXT layer's K / V cache rows into L2, so that the
-    // attention kernel two stages later streams them from L2 instead of HBM (the rows of earlier positions do not
-    // change; HBM is otherwise idle during the GEMM stages of the chain).
-    if (p.pf.k != nullptr) {
-      const int pos = *p.pf.pos_ptr;
-      const unsigned bytes = static_cast<unsigned>(pos) * p.pf.row_bytes;
-      const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-      const int ncta = gridDim.x * gridDim.y * gridDim.z;
-      if (bytes >= 16)
-        for (int run = cta * 32 + lane; run < 2 * p.pf.pairs; run += ncta * 32) {
-          const char* base = (run < p.pf.pairs ? p.pf.k : p.pf.v) + static_cast<long long>(run % p.pf.pairs) * p.pf.run_stride;
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"(bytes) : "memory");
-        }
-    }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(FBM, FBN);
@@ -133,8 +117,12 @@ gemm_decode_fold_kernel(const __grid_constant__ CUtensorMap tmW, const FoldParam
     // constants first (weights-like: safe before the dependency resolves).  They go to shared memory, not registers:
     // with 64 more live registers per thread only one CTA fits an SM and a 256-CTA grid takes two waves.
     for (int i = et; i < nkb * FBK; i += 32 * SW) {
-      s_c0[i] = __ldg((MODE == FOLD_LN ? p.gamma : p.in.sw) + kb0 * FBK + i);
-      if (MODE == FOLD_GELU) s_c1[i] = __ldg(p.in.bp + kb0 * FBK + i);
+      const float c0 = __ldg((MODE == FOLD_LN ? p.gamma : p.in.sw) + kb0 * FBK + i);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(s_c0 + i)), "f"(c0) : "memory");
+      if (MODE == FOLD_GELU) {
+        const float c1 = __ldg(p.in.bp + kb0 * FBK + i);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(s_c1 + i)), "f"(c1) : "memory");
+      }
     }
     pdl_wait();
     float v[RPT][F_MAX_KB][8];
@@ -227,7 +215,7 @@ gemm_decode_fold_kernel(const __grid_constant__ CUtensorMap tmW, const FoldParam
             if (MODE == FOLD_LN) o[e] = v[j][kb][e] * cg[e];
             else {
               const float pre = fmaf(rs[j], fmaf(-mu[j], cg[e], v[j][kb][e]), cb[e]);
-              o[e] = p.exact_erf ? gelu_erf(pre) : gelu_erf_fast(pre);
+              o[e] = gelu_erf_fast(pre);
             }
             if (n0 + rl >= p.B) o[e] = 0.f;
           }
@@ -341,7 +329,7 @@ int gpt_fold_apply(float* out, int B, int N, const LnFold& f, cudaStream_t strea
 
 int gemm_decode_fold(int mode, const void* W, int Nw, int K, const float* src, int B, const float* gamma,
                      float2* stats_out, int stats_stride, const LnFold* in, const float* bias, float* out, long long ldo,
-                     int kbps, int staging_warps, int bn, bool pdl, cudaStream_t stream, const KvPrefetch* pf) {
+                     int kbps, int staging_warps, int bn, bool pdl, cudaStream_t stream) {
   MGV_REQUIRE(W && src && out && Nw >= 1 && B >= 1, "fold decode gemm: bad arguments");
   MGV_REQUIRE(K % FBK == 0 && kbps >= 1 && kbps <= F_MAX_KB, "fold decode gemm: K=%d kbps=%d", K, kbps);
   const int splits = ceil_div(K / FBK, kbps);
@@ -349,7 +337,6 @@ int gemm_decode_fold(int mode, const void* W, int Nw, int K, const float* src, i
   memset(&p, 0, sizeof(p));
   p.Nw = Nw; p.B = B; p.K = K; p.kbps = kbps;
   p.src = src; p.bias = bias; p.out = out; p.ldo = ldo;
-  if (pf) p.pf = *pf;
   CUtensorMap tmW;
   MGV_TRY(make_tmap_2d_bf16(&tmW, W, K, Nw, static_cast<uint64_t>(K) * 2, FBK, FBM));
   const bool wide = staging_warps >= 8 || bn == 64;
@@ -363,8 +350,6 @@ int gemm_decode_fold(int mode, const void* W, int Nw, int K, const float* src, i
   MGV_REQUIRE(mode == FOLD_GELU && in && in->stats && in->sw && in->bp && in->nparts >= 1 && in->dim >= 1,
               "fold decode gemm: GELU mode needs the producer's statistics and fold vectors");
   p.in = *in;
-  static const bool exact_erf = getenv("MGV_FOLD_EXACT_ERF") != nullptr && atoi(getenv("MGV_FOLD_EXACT_ERF")) != 0;
-  p.exact_erf = exact_erf ? 1 : 0;
   if (bn == 64) return launch_fold<FOLD_GELU, 8, 64>(tmW, p, splits, pdl, stream);
   return wide ? launch_fold<FOLD_GELU, 8, 32>(tmW, p, splits, pdl, stream) : launch_fold<FOLD_GELU, 4, 32>(tmW, p, splits, pdl, stream);
 }

@@ -71,22 +71,13 @@ int gemm_decode_fullk(const void* W, int Nw, int K, const void* X_bf16, int B, c
 // ---- decode-step GEMMs that absorb the LayerNorm / GELU stage in front of them (gemm_decode_fold.cu)
 // (LnFold: mgv_common.cuh)
 enum FoldMode : int { FOLD_LN = 0, FOLD_GELU = 1 };
-// L2 prefetch request carried by a fold GEMM: rows [0, *pos_ptr) of `pairs` (sequence, head) runs of the K and the V cache
-struct KvPrefetch {
-  const char* k = nullptr;
-  const char* v = nullptr;
-  const int* pos_ptr = nullptr;
-  int pairs = 0;
-  unsigned row_bytes = 0;          // bytes of one cache row (head dim * 2)
-  long long run_stride = 0;        // bytes between two (sequence, head) runs
-};
 // mode FOLD_LN  : out[b, n] += sum_k W[n,k] bf16(gamma[k] src[b,k]);  stats_out[z][b] = partial row statistics of src
 // mode FOLD_GELU: out[b, n] += sum_k W[n,k] bf16(gelu(rstd_b (src[b,k] - mu_b in.sw[k]) + in.bp[k])) (+ bias[n])
 // W bf16 [Nw, K]; src fp32 [B, K]; out fp32 [B, ldo] (holds zeros / the residual); kbps = 64-wide k-blocks per CTA (<= 4);
 // bn = sequences per CTA (32 or 64).
 int gemm_decode_fold(int mode, const void* W, int Nw, int K, const float* src, int B, const float* gamma,
                      float2* stats_out, int stats_stride, const LnFold* in, const float* bias, float* out, long long ldo,
-                     int kbps, int staging_warps, int bn, bool pdl, cudaStream_t stream, const KvPrefetch* pf = nullptr);
+                     int kbps, int staging_warps, int bn, bool pdl, cudaStream_t stream);
 // sw[n] = sum_k W[n,k] gamma[k];  bp[n] = sum_k W[n,k] beta[k] + bias[n] (bias may be null)
 int gpt_fold_prepare(const void* W, int N, int K, const float* gamma, const float* beta, const float* bias, float* sw,
                      float* bp, cudaStream_t stream);

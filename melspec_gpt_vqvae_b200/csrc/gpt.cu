@@ -96,13 +96,13 @@ struct Gpt {
   float *sw_head = nullptr, *bp_head = nullptr;
   float2 *stats1 = nullptr, *stats2 = nullptr;   // [FOLD_MAX_PARTS][dec_B] partial LayerNorm statistics (ln1 / ln_f, ln2)
   int fold_sw = 4, fold_sw_gelu = 8;             // staging warps of the fold GEMMs (MGV_FOLD_SW=a,b)
-  bool kv_prefetch = true;                       // MGV_KV_PREFETCH=0: no L2 prefetch of the next layer's KV rows
   int fold_bn = 32, fold_bn2 = 32;               // sequences per CTA of the FOLD_LN / FOLD_GELU GEMMs (MGV_FOLD_BN=a,b)
   cudaStream_t gstream[MAX_GROUPS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {};
   bool pdl = false;
   DecodeTiles tiles;
   long long launches = 0;  // kernels launched by the last forward / generate call
+  float* step_logits = nullptr;   // one-shot request (gpt_set_step_logits): per-step logits of the next generate call
 
   __nv_bfloat16* kcache(int l) const {
     return kv + (static_cast<size_t>(l) * 2) * dec_B * nh * Tmax * GPT_HEAD_DIM;
@@ -311,8 +311,6 @@ int gpt_create(const GptConfig* cfg, Gpt** out) {
   }
   const char* fe = getenv("MGV_DECODE_FOLD");
   if (fe) g->use_fold = atoi(fe) != 0;
-  const char* kp = getenv("MGV_KV_PREFETCH");
-  if (kp) g->kv_prefetch = atoi(kp) != 0;
   const char* fb = getenv("MGV_FOLD_BN");
   if (fb) {
     int a = 0, b = 0;
@@ -549,22 +547,13 @@ int enqueue_group_step(Gpt* g, int b0, int B, const SampleArgs& sa, float* att_o
       const bool pdl0 = g->pdl && (l > 0 || first_kernel_pdl);
       MGV_TRY(gemm_decode_fold(FOLD_LN, w.wqkv, 3 * C, C, dx, B, w.ln1_w, st1, sstride, nullptr, nullptr, dqkv32, 3 * C, kq,
                                g->fold_sw, fbn, pdl0, s));
+      // (the attention kernel also clears the FC1 accumulator: its last reader, the previous block's FC2, is complete)
       MGV_TRY(gpt_attention_decode(dqkv32, B, g->nh, sa.pos_ptr, g->kcache(l) + kv_off, g->vcache(l) + kv_off, g->Tmax, dy,
                                    (l == g->L - 1) ? att_out : nullptr, att_T, true, dh32,
                                    static_cast<long long>(B) * 4 * C, s, g->pdl, &f1));
       MGV_TRY(decode_gemm(g, dy, w.wproj, w.bproj, B, C, C, tl.proj_split, EPI_F32_RESID, dx, dx, s));
-      KvPrefetch pf;
-      if (g->kv_prefetch) {     // K / V rows of the layer whose attention runs next (layer 0 of the next position after the last)
-        const int ln = (l + 1) % g->L;
-        pf.k = reinterpret_cast<const char*>(g->kcache(ln) + kv_off);
-        pf.v = reinterpret_cast<const char*>(g->vcache(ln) + kv_off);
-        pf.pos_ptr = sa.pos_ptr;
-        pf.pairs = B * g->nh;
-        pf.row_bytes = GPT_HEAD_DIM * 2;
-        pf.run_stride = static_cast<long long>(g->Tmax) * GPT_HEAD_DIM * 2;
-      }
       MGV_TRY(gemm_decode_fold(FOLD_LN, w.wfc1, 4 * C, C, dx, B, w.ln2_w, st2, sstride, nullptr, nullptr, dh32, 4 * C, kq,
-                               g->fold_sw, fbn, g->pdl, s, g->kv_prefetch ? &pf : nullptr));
+                               g->fold_sw, fbn, g->pdl, s));
       MGV_TRY(gemm_decode_fold(FOLD_GELU, w.wfc2, C, 4 * C, dh32, B, nullptr, nullptr, 0, &f2, w.bfc2, dx, C, kf2,
                                g->fold_sw_gelu, fbn2, g->pdl, s));
       g->launches += 4;
@@ -732,7 +721,10 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   sa.pos_ptr = g->d_state + 8;
   sa.tokens = g->dtokens; sa.tokens_ld = tld; sa.m = m;
   sa.tok_emb = g->tok_emb; sa.pos_emb = g->pos_emb; sa.block_size = g->cfg.block_size;
-  sa.x_next = g->dx; sa.logits_out = nullptr;
+  sa.x_next = g->dx;
+  sa.logits_out = g->step_logits; sa.logits_step_stride = static_cast<long long>(B) * g->V; sa.logits_pos0 = T0 - 1;
+  const bool want_step_logits = g->step_logits != nullptr;
+  g->step_logits = nullptr;
   sa.done_counter = reinterpret_cast<unsigned int*>(g->d_state + 9);
 
   MGV_TRY(prepare_fold(g, s));
@@ -742,7 +734,7 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
     // the decode-step graph only depends on (B, m, sampler settings) and on handle-owned buffers, so it is
     // captured once and replayed for every position of every later call with the same settings; a request for
     // the attention map (caller-owned buffer) gets a one-off graph
-    const bool cacheable = att_out == nullptr;
+    const bool cacheable = att_out == nullptr && !want_step_logits;
     const bool hit = cacheable && g->graph_exec && g->graph_key.B == B && g->graph_key.m == m &&
                      g->graph_key.top_k == top_k && g->graph_key.do_sample == do_sample &&
                      g->graph_key.temperature == temperature;
@@ -811,5 +803,11 @@ int gpt_cross_entropy(Gpt* g, const float* logits, const long long* targets, lon
 }
 
 long long gpt_last_launches(const Gpt* g) { return g ? g->launches : 0; }
+
+int gpt_set_step_logits(Gpt* g, float* buf) {
+  MGV_REQUIRE(g, "gpt_set_step_logits: null handle");
+  g->step_logits = buf;
+  return MGV_OK;
+}
 
 }  // namespace mgv

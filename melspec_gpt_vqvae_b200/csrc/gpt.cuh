@@ -28,5 +28,8 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
 int gpt_cross_entropy(Gpt* g, const float* logits, const long long* targets, long long rows, int V, float* loss,
                       cudaStream_t s);
 long long gpt_last_launches(const Gpt* g);
+// one-shot: the NEXT gpt_generate call also writes the logits of every step (after temperature, before top-k) to
+// buf [steps, B, V] fp32 (device, caller-owned); pass nullptr to cancel
+int gpt_set_step_logits(Gpt* g, float* buf);
 
 }  // namespace mgv

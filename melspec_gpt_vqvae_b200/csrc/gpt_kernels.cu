@@ -657,7 +657,7 @@ sample_step_kernel(const SampleArgs a) {
     const float l = __fdiv_rn(raw, a.temperature);
     lrow[i] = 0.f;
     sl[i] = l;
-    if (a.logits_out) a.logits_out[static_cast<long long>(b) * a.V + i] = l;
+    if (a.logits_out) a.logits_out[static_cast<long long>(pos - a.logits_pos0) * a.logits_step_stride + static_cast<long long>(a.row0 + b) * a.V + i] = l;
   }
   __syncthreads();
 

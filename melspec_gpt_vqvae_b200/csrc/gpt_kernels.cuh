@@ -54,7 +54,10 @@ struct SampleArgs {
   const float* pos_emb;
   int block_size;
   float* x_next;           // [B, C]: embedding of the sampled token at position pos+1
-  float* logits_out;       // optional [B, V]: logits of this step (after temperature, before top-k)
+  float* logits_out;       // optional [steps, logits_step_stride]: logits of every step (after temperature, before top-k),
+                           // step index = position - logits_pos0, row b at offset (row0 + b) * V
+  long long logits_step_stride;
+  int logits_pos0;
   unsigned int* done_counter;  // device scratch (zero-initialised) used to advance *pos_ptr once per step
   LnFold fold;             // folded ln_f (stats == nullptr: logits_acc already holds the logits)
 };

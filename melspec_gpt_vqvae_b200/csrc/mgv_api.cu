@@ -202,6 +202,11 @@ int mgv_gpt_cross_entropy(mgv_gpt_t* g, const float* logits, const int64_t* targ
   MGV_API_END
 }
 int64_t mgv_gpt_last_launches(const mgv_gpt_t* g) { return gpt_last_launches(reinterpret_cast<const Gpt*>(g)); }
+int mgv_gpt_set_step_logits(mgv_gpt_t* g, float* buf) {
+  MGV_API_BEGIN
+  return gpt_set_step_logits(reinterpret_cast<Gpt*>(g), buf);
+  MGV_API_END
+}
 
 int mgv_vqvae_create(int num_embeddings, int embedding_dim, mgv_vqvae_t** out) {
   MGV_API_BEGIN
