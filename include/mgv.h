@@ -52,7 +52,8 @@ int mgv_device_check(void);
  * codebook: fp32 (K, C) = _embedding.weight;  C in {64,128,192,256};  K up to 65536: codebooks beyond 128 codes
  *   (e.g. the reference's 1024-code VGGSound variant) are searched in passes of 128 codes, lowest index still wins;
  * idx_out: int64 (B*H*W) in (b, h, w) order (= encoding_indices.squeeze(1));
- * dmin_out: optional fp32 (B*H*W), the winning distance.
+ * dmin_out: fp32 (B*H*W), the winning distance; optional for num_embeddings <= 128, REQUIRED beyond (the 128-code
+ * passes hand the running minimum to each other through it).
  * Distances are fp32, d = (|x|^2 + |e|^2) - 2<x,e>, every sum a sequential fmaf chain over
  * the channel index; first index wins ties (torch.argmin).  oracle/vq_oracle.c restates it. */
 int mgv_vq_argmin(const float* z_bchw, const float* codebook, int B, int C, int HW, int K,
@@ -128,6 +129,11 @@ int mgv_gpt_cross_entropy(mgv_gpt_t* g, const float* logits, const int64_t* targ
 
 /* number of kernels libmgv launched in the last forward / generate call on this handle */
 int64_t mgv_gpt_last_launches(const mgv_gpt_t* g);
+
+/* Deterministic decode switch.  The default decode loop reduces split-K partial sums with fp32 atomics whose order depends
+ * on CTA timing, so sampled tokens can differ run to run at near-ties (the reference's greedy path is deterministic).
+ * on != 0 selects a schedule in which every decode GEMM owns its full K: bit-reproducible, about 2x slower. */
+int mgv_gpt_set_deterministic(mgv_gpt_t* g, int on);
 
 /* One-shot inspection hook for parity tests: the NEXT mgv_gpt_generate call on this handle also writes the logits of
  * every decode step (after the temperature division, before top-k; reference transformer/minGPT.py:346) to

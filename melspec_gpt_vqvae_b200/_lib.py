@@ -35,6 +35,7 @@ SIGNATURES = {
     "mgv_gpt_cross_entropy": (I, [VP, VP, VP, I64, I, VP, VP]),
     "mgv_gpt_last_launches": (I64, [VP]),
     "mgv_gpt_set_step_logits": (I, [VP, VP]),
+    "mgv_gpt_set_deterministic": (I, [VP, I]),
     "mgv_vqvae_create": (I, [I, I, ctypes.POINTER(VP)]),
     "mgv_vqvae_destroy": (I, [VP]),
     "mgv_vqvae_load_weight": (I, [VP, ctypes.c_char_p, VP, I64, VP]),
@@ -89,6 +90,7 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device)."""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

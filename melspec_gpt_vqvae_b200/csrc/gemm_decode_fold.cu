@@ -265,11 +265,13 @@ template <int MODE, int SW, int FBN>
 int launch_fold(const CUtensorMap& tmW, const FoldParams& p, int splits, bool pdl, cudaStream_t stream) {
   constexpr int FSTAGE = FA_BYTES + FBN * FBK * 2;
   const size_t smem = static_cast<size_t>(F_MAX_KB) * FSTAGE + 64 + 2 * F_MAX_KB * FBK * 4 + 1024;
-  // (cudaFuncSetAttribute is cheap and per device: set on every call instead of caching a per-process flag)
-  MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_decode_fold_kernel<MODE, SW, FBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-  MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_decode_fold_kernel<MODE, SW, FBN>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
+  static unsigned long long attr_mask = 0;   // per device (and per template instantiation)
+  if (first_use_on_this_device(attr_mask)) {
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_decode_fold_kernel<MODE, SW, FBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_decode_fold_kernel<MODE, SW, FBN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+  }
   LaunchCfg lc(dim3(ceil_div(p.Nw, FBM), ceil_div(p.B, FBN), splits), dim3(64 + 32 * SW), smem, stream, pdl);
   MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_decode_fold_kernel<MODE, SW, FBN>, tmW, p));
   return MGV_OK;

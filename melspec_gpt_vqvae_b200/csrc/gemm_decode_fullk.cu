@@ -167,12 +167,11 @@ gemm_decode_fullk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_c
 template <int KG>
 int launch_fullk(const CUtensorMap& tmW, const CUtensorMap& tmX, const FkParams& p, bool pdl, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(FK_GROUPS) * KG * FK_KB_BYTES + (2 * FK_GROUPS + 1) * 8 + 16 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;   // per device (and per template instantiation)
+  if (first_use_on_this_device(attr_mask)) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_decode_fullk_kernel<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_decode_fullk_kernel<KG>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
   }
   LaunchCfg lc(dim3(ceil_div(p.Nw, FK_BM), ceil_div(p.B, FK_BN)), dim3(FK_THREADS), smem, stream, pdl);
   MGV_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, gemm_decode_fullk_kernel<KG>, tmW, tmX, p));

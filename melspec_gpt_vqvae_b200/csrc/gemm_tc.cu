@@ -909,13 +909,12 @@ int launch_tc(const GemmArgs& a, KParams& p) {
   }
   MGV_TRY(make_tmap_2d_bf16(&tmB, a.B, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, BN));
 
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;   // per device (and per template instantiation)
+  if (first_use_on_this_device(attr_mask)) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, DECODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // ask for the full shared-memory carve-out so that several CTAs (small rings) can share an SM
     MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, DECODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
   }
   dim3 grid;
   if (a.a_mode == A_PLAIN)
@@ -949,12 +948,11 @@ int launch_persist(const GemmArgs& a, KParams& p) {
   }
   MGV_TRY(make_tmap_2d_bf16(&tmB, a.B, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, BN));
   const int n_tiles = ceil_div(a.N, BN);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;   // per device (and per template instantiation)
+  if (first_use_on_this_device(attr_mask)) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     MGV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, MT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
   }
   const int total = ceil_div(m_tiles, MT) * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();

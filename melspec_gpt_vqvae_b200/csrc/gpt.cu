@@ -102,6 +102,9 @@ struct Gpt {
   bool pdl = false;
   DecodeTiles tiles;
   long long launches = 0;  // kernels launched by the last forward / generate call
+  bool deterministic = false, saved_fold = true;   // gpt_set_deterministic
+  DecodeTiles saved_tiles;
+  int saved_groups = 1;
   float* step_logits = nullptr;   // one-shot request (gpt_set_step_logits): per-step logits of the next generate call
 
   __nv_bfloat16* kcache(int l) const {
@@ -668,6 +671,10 @@ int gpt_generate(Gpt* g, const long long* x0, int B, int t0, const float* prefix
   // assert x.size(1) + cond_size <= block_size at every step (minGPT.py:336)
   MGV_REQUIRE(steps == 0 || t0 + steps - 1 + m <= g->cfg.block_size,
               "sample: context %d + cond %d exceeds block_size %d", t0 + steps - 1, m, g->cfg.block_size);
+  // KV-cache decoding equals the reference's per-step full forward only for a causal mask: with an unmasked prefix
+  // (minGPT.py:67-68) rows below n_unmasked would re-attend to every later token at every step
+  MGV_REQUIRE(g->cfg.n_unmasked <= 1, "gpt_generate: n_unmasked=%d > 1 is not supported by the KV-cache decode loop "
+              "(the reference recomputes the prefix-unmasked rows at every step)", g->cfg.n_unmasked);
   if (B == 0) return MGV_OK;
   g->launches = 0;
   cudaStream_t s = g->stream;
@@ -803,6 +810,30 @@ int gpt_cross_entropy(Gpt* g, const float* logits, const long long* targets, lon
 }
 
 long long gpt_last_launches(const Gpt* g) { return g ? g->launches : 0; }
+
+// Deterministic decode: every decode GEMM owns its full K (no split-K reductions, whose fp32 summation order depends on
+// CTA timing) through the separate-LayerNorm chain; same results run to run and independent of the batch size.
+int gpt_set_deterministic(Gpt* g, int on) {
+  MGV_REQUIRE(g, "gpt_set_deterministic: null handle");
+  const bool want = on != 0;
+  if (want == g->deterministic) return MGV_OK;
+  g->deterministic = want;
+  if (want) {
+    g->saved_fold = g->use_fold;
+    g->saved_tiles = g->tiles;
+    g->saved_groups = g->groups;
+    g->use_fold = false;
+    g->groups = 1;
+    g->tiles.qkv_split = g->tiles.proj_split = g->tiles.fc1_split = g->tiles.fc2_split = g->tiles.head_split = 1;
+  } else {
+    g->use_fold = g->saved_fold;
+    g->tiles = g->saved_tiles;
+    g->groups = g->saved_groups;
+  }
+  if (g->graph_exec) { cudaGraphExecDestroy(g->graph_exec); g->graph_exec = nullptr; }
+  if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }
+  return MGV_OK;
+}
 
 int gpt_set_step_logits(Gpt* g, float* buf) {
   MGV_REQUIRE(g, "gpt_set_step_logits: null handle");

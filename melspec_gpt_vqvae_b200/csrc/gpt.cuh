@@ -31,5 +31,7 @@ long long gpt_last_launches(const Gpt* g);
 // one-shot: the NEXT gpt_generate call also writes the logits of every step (after temperature, before top-k) to
 // buf [steps, B, V] fp32 (device, caller-owned); pass nullptr to cancel
 int gpt_set_step_logits(Gpt* g, float* buf);
+// on != 0: decode without split-K reductions (bit-reproducible run to run, slower); 0 restores the default schedule
+int gpt_set_deterministic(Gpt* g, int on);
 
 }  // namespace mgv

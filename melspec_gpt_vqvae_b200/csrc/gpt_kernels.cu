@@ -853,8 +853,8 @@ int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_
   if (B == 0) return MGV_OK;
   const int kpad = ceil_div(T, FA_BN) * FA_BN;
   const size_t smem = static_cast<size_t>(2 * kpad) * FA_LD * sizeof(__nv_bfloat16);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;   // per device (and per template instantiation)
+  if (first_use_on_this_device(attr_mask)) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         2 * FA_MAXK * FA_LD * 2));
     MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -863,7 +863,6 @@ int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_
                                         2 * FA_MAXK * FA_LD * 2));
     MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
   }
   if (att != nullptr)
     attn_prefill_kernel<true><<<B * nh, FA_THREADS, smem, s>>>(qkv, B, T, nh, n_unmasked, y, att, att_T, kcache, vcache, Tmax);

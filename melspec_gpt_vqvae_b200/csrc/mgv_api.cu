@@ -37,14 +37,24 @@ int check_device() {
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& slot = n[dev & 63];
+  if (slot == 0) {
+    cudaDeviceGetAttribute(&slot, cudaDevAttrMultiProcessorCount, dev);
+    if (slot <= 0) slot = 148;
   }
-  return n;
+  return slot;
+}
+
+bool first_use_on_this_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
 }
 
 // ------------------------------------------------------------------ tensor maps
@@ -202,6 +212,11 @@ int mgv_gpt_cross_entropy(mgv_gpt_t* g, const float* logits, const int64_t* targ
   MGV_API_END
 }
 int64_t mgv_gpt_last_launches(const mgv_gpt_t* g) { return gpt_last_launches(reinterpret_cast<const Gpt*>(g)); }
+int mgv_gpt_set_deterministic(mgv_gpt_t* g, int on) {
+  MGV_API_BEGIN
+  return gpt_set_deterministic(reinterpret_cast<Gpt*>(g), on);
+  MGV_API_END
+}
 int mgv_gpt_set_step_logits(mgv_gpt_t* g, float* buf) {
   MGV_API_BEGIN
   return gpt_set_step_logits(reinterpret_cast<Gpt*>(g), buf);

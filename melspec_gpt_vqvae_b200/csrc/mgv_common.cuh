@@ -45,7 +45,10 @@ const char* get_error();
   } while (0)
 
 int check_device();      // MGV_OK iff the current device is compute capability 10.x
-int num_sms();
+int num_sms();           // SM count of the CURRENT device (cached per device)
+// true the first time it is called for `mask` on the current device: per-device one-off setup such as
+// cudaFuncSetAttribute (function attributes are per device, and a process may drive several GPUs)
+bool first_use_on_this_device(unsigned long long& mask);
 
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -283,12 +283,6 @@ __global__ void vq_gather_kernel(const long long* __restrict__ idx, const float*
 
 }  // namespace
 
-namespace {
-// scratch for the running minimum distance of multi-pass (K > 128) searches when the caller passes no dmin buffer
-float* g_dmin_scratch = nullptr;
-long long g_dmin_cap = 0;
-}  // namespace
-
 int vq_argmin(const float* z, const float* codebook, int B, int D, int HW, int K, long long* idx_out, float* dmin_out,
               cudaStream_t stream) {
   MGV_REQUIRE(B >= 0 && HW > 0, "vq_argmin: B=%d HW=%d", B, HW);
@@ -300,24 +294,13 @@ int vq_argmin(const float* z, const float* codebook, int B, int D, int HW, int K
   const int num_tiles = static_cast<int>((N + VQ_TILE_V - 1) / VQ_TILE_V);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   const size_t smem = (static_cast<size_t>(D) * VQ_MAX_K + VQ_MAX_K + 2 * VQ_KC * VQ_TILE_V) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;   // per device (and per template instantiation)
+  if (first_use_on_this_device(attr_mask)) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
   }
-  if (K > VQ_MAX_K && dmin_out == nullptr) {   // the passes hand the running minimum to each other
-    if (g_dmin_cap < N) {
-      if (g_dmin_scratch) {
-        MGV_CHECK_CUDA(cudaStreamSynchronize(stream));   // (rare: growth only) earlier launches may still use the old block
-        cudaFree(g_dmin_scratch);
-        g_dmin_scratch = nullptr;
-        g_dmin_cap = 0;
-      }
-      MGV_CHECK_CUDA(cudaMalloc(&g_dmin_scratch, static_cast<size_t>(N) * sizeof(float)));
-      g_dmin_cap = N;
-    }
-    dmin_out = g_dmin_scratch;
-  }
+  // codebooks beyond one 128-code pass: the passes hand the running minimum to each other through dmin_out
+  // (caller-owned, so that concurrent streams / devices never share scratch memory)
+  MGV_REQUIRE(K <= VQ_MAX_K || dmin_out != nullptr, "vq_argmin: num_embeddings=%d > %d needs a dmin buffer of B*HW floats", K, VQ_MAX_K);
   for (int code0 = 0; code0 < K; code0 += VQ_MAX_K) {
     const int kc = (K - code0 < VQ_MAX_K) ? K - code0 : VQ_MAX_K;
     vq_argmin_kernel<<<grid, VQ_THREADS, smem, stream>>>(z, codebook, B, D, HW, kc, idx_out, dmin_out, code0, code0 > 0 ? 1 : 0);

@@ -659,12 +659,11 @@ int vqvae_spatial_attention(const __nv_bfloat16* qkv, int N, int T, int C, __nv_
   constexpr int RS = 512 / 2 + 4;
   const int Tpad = ceil_div(T, SA_KCH) * SA_KCH;
   const size_t smem = (static_cast<size_t>(SA_ROWS) * RS + SA_KCH * RS) * 4 + static_cast<size_t>(SA_ROWS) * (Tpad + 1) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;   // per device (and per template instantiation)
+  if (first_use_on_this_device(attr_mask)) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(spatial_attn_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MGV_CHECK_CUDA(cudaFuncSetAttribute(spatial_attn_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
   }
   MGV_REQUIRE(smem <= 200 * 1024, "spatial_attention: T=%d needs too much shared memory", T);
   spatial_attn_kernel<512><<<dim3(ceil_div(T, SA_ROWS), N), SA_THREADS, smem, s>>>(qkv, T, o);

@@ -81,12 +81,13 @@ class GPTDecoder(nn.Module):
         if steps == 0:
             raise UnboundLocalError("local variable 'att' referenced before assignment")   # as the reference (:123)
         Tf = m + t0 + steps - 1
-        out = torch.empty(B, t0 + steps, dtype=torch.int64, device=x.device)
-        att = torch.empty(B, tr.config.n_head, Tf, Tf, dtype=torch.float32, device=x.device) if self.return_attention else None
         seed = int(self.sample_seed) & 0xFFFFFFFFFFFFFFFF
         self.sample_seed = (int(self.sample_seed) * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
-        _lib.check(_lib.load().mgv_gpt_generate(
-            tr._handle(), _lib.ptr(x) if t0 > 0 else None, B, t0, _lib.ptr(emb), None, m, int(steps), float(temperature),
-            1 if sample else 0, int(top_k) if top_k is not None else 0, seed, _lib.ptr(out), _lib.ptr(att), 1,
-            _lib.stream_ptr()), "mgv_gpt_generate")
+        with tr._on_device():
+            out = torch.empty(B, t0 + steps, dtype=torch.int64, device=x.device)
+            att = torch.empty(B, tr.config.n_head, Tf, Tf, dtype=torch.float32, device=x.device) if self.return_attention else None
+            _lib.check(_lib.load().mgv_gpt_generate(
+                tr._handle(), _lib.ptr(x) if t0 > 0 else None, B, t0, _lib.ptr(emb), None, m, int(steps), float(temperature),
+                1 if sample else 0, int(top_k) if top_k is not None else 0, seed, _lib.ptr(out), _lib.ptr(att), 1,
+                _lib.stream_ptr(x.device)), "mgv_gpt_generate")
         return out, (att.detach().cpu() if att is not None else None)

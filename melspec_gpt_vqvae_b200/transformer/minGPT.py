@@ -10,8 +10,12 @@ libmgv (include/mgv.h):
   Lit_minGPT.decode_to_img         -> code_reader + mgv_vqvae_decode_codes
   GPT.forward(targets=...) loss    -> mgv_gpt_cross_entropy
 
-Inference (eval mode) only: the reference's training step is a "next" row (SURVEY.md
-section 8(f)).  No CPU fallback.
+The forward / sample paths are inference (eval mode) kernels; the teacher-forced training step lives in
+transformer/train_step.py.  No CPU fallback.
+
+Device handling: every libmgv call runs with the device that holds the parameters made current
+(`torch.cuda.device(p.device)`), on that device's current torch stream, and the handle is rebuilt when the
+parameters move to another GPU -- a model on cuda:1 works while cuda:0 is current, as with the reference.
 """
 import ctypes
 import logging
@@ -31,6 +35,11 @@ except Exception:  # pragma: no cover
     _LitBase = nn.Module
 
 logger = logging.getLogger(__name__)
+
+
+def _no_callback(k):
+    """default `callback` of Lit_minGPT.sample (reference :293: `lambda k: None`)"""
+    return None
 
 _HOT_PATH_ONLY = ("this submodule only owns parameters; the computation runs fused inside libmgv -- call "
                   "GPT.forward / Lit_minGPT.sample instead")
@@ -115,6 +124,8 @@ class GPT(nn.Module):
         self.config = config
         self._mgv_handle = None
         self._mgv_sig = None
+        self._mgv_dev = None
+        self._deterministic = False
         logger.info("number of parameters: %e", sum(p.numel() for p in self.parameters()))
 
     def get_block_size(self):
@@ -135,10 +146,13 @@ class GPT(nn.Module):
         return emb.num_embeddings if emb is not None else 0
 
     def _handle(self):
+        """libmgv handle for the device that holds the parameters (call with that device current: `_on_device`)."""
         p = self.head.weight
         if not p.is_cuda:
             raise RuntimeError("GPT: parameters are on %s; libmgv has no CPU path -- call .to('cuda')" % p.device)
         L = _lib.load()
+        if self._mgv_handle is not None and self._mgv_dev != p.device:
+            self._release_handle()                     # the module moved to another GPU
         if self._mgv_handle is None:
             cfg = _lib.GptConfig(vocab_size=self.config.vocab_size, block_size=self.block_size,
                                  n_layer=self.config.n_layer, n_head=self.config.n_head, n_embd=self.config.n_embd,
@@ -147,25 +161,68 @@ class GPT(nn.Module):
             h = ctypes.c_void_p()
             _lib.check(L.mgv_gpt_create(ctypes.byref(cfg), ctypes.byref(h)), "mgv_gpt_create")
             self._mgv_handle = h
+            self._mgv_dev = p.device
             self._mgv_sig = None
+            if self._deterministic:
+                _lib.check(L.mgv_gpt_set_deterministic(h, 1), "mgv_gpt_set_deterministic")
         sig = _params_signature(self)
         if sig != self._mgv_sig:
-            st = _lib.stream_ptr()
+            st = _lib.stream_ptr(p.device)
             for k, t in self.state_dict().items():
                 if k.endswith("attn.mask"):
                     continue
                 t32 = t.detach().to(torch.float32).contiguous()
                 _lib.check(L.mgv_gpt_load_weight(self._mgv_handle, k.encode(), _lib.ptr(t32), t32.numel(), st),
                            "mgv_gpt_load_weight(%s)" % k)
-            torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream(p.device).synchronize()
             self._mgv_sig = sig
         return self._mgv_handle
 
+    def _on_device(self):
+        """context manager: the parameters' GPU is the current device while libmgv is called"""
+        p = self.head.weight
+        if not p.is_cuda:
+            raise RuntimeError("GPT: parameters are on %s; libmgv has no CPU path -- call .to('cuda')" % p.device)
+        return torch.cuda.device(p.device)
+
+    def refresh_weights(self):
+        """Re-pack the bf16 weight copies inside libmgv on the next call.  Needed only after edits that bypass autograd's
+        version counter (`p.data.copy_()`, `p.data.mul_()` ...): load_state_dict, .to() and ordinary in-place ops are
+        detected automatically."""
+        self._mgv_sig = None
+
+    @property
+    def deterministic(self):
+        return self._deterministic
+
+    @deterministic.setter
+    def deterministic(self, on):
+        """True: decode without split-K reductions (bit-reproducible run to run like the reference's greedy path, slower)."""
+        self._deterministic = bool(on)
+        if self._mgv_handle is not None:
+            with torch.cuda.device(self._mgv_dev):
+                _lib.check(_lib.load().mgv_gpt_set_deterministic(self._mgv_handle, 1 if on else 0), "mgv_gpt_set_deterministic")
+
+    def _release_handle(self):
+        if getattr(self, "_mgv_handle", None) is not None:
+            try:
+                with torch.cuda.device(self._mgv_dev):
+                    _lib.load().mgv_gpt_destroy(self._mgv_handle)
+            finally:
+                self._mgv_handle = None
+                self._mgv_sig = None
+
+    def __getstate__(self):
+        # the libmgv handle is a process-local cache: drop it so that copy.deepcopy / pickle / torch.save(model) work
+        state = self.__dict__.copy()
+        state["_mgv_handle"] = None
+        state["_mgv_sig"] = None
+        state["_mgv_dev"] = None
+        return state
+
     def __del__(self):
         try:
-            if getattr(self, "_mgv_handle", None) is not None:
-                _lib.load().mgv_gpt_destroy(self._mgv_handle)
-                self._mgv_handle = None
+            self._release_handle()
         except Exception:
             pass
 
@@ -192,10 +249,14 @@ class GPT(nn.Module):
         assert T <= self.block_size, "Cannot forward, model block size is exhausted."      # reference :178
         vout = self.head.out_features
         nh = self.config.n_head
-        logits = torch.empty(B, T, vout, dtype=torch.float32, device=idx.device)
-        att = torch.empty(B, nh, T, T, dtype=torch.float32, device=idx.device)
-        _lib.check(_lib.load().mgv_gpt_forward(self._handle(), _lib.ptr(idx), B, t, _lib.ptr(emb), _lib.ptr(cls), m,
-                                               _lib.ptr(logits), _lib.ptr(att), _lib.stream_ptr()), "mgv_gpt_forward")
+        dev = self.head.weight.device
+        if idx.device != dev:
+            raise RuntimeError("GPT.forward: idx is on %s but the parameters are on %s" % (idx.device, dev))
+        with self._on_device():
+            logits = torch.empty(B, T, vout, dtype=torch.float32, device=dev)
+            att = torch.empty(B, nh, T, T, dtype=torch.float32, device=dev)
+            _lib.check(_lib.load().mgv_gpt_forward(self._handle(), _lib.ptr(idx), B, t, _lib.ptr(emb), _lib.ptr(cls), m,
+                                                   _lib.ptr(logits), _lib.ptr(att), _lib.stream_ptr(dev)), "mgv_gpt_forward")
         return logits, att
 
     @torch.no_grad()
@@ -219,13 +280,15 @@ class GPT(nn.Module):
         t = targets1d.detach().to(device=lg.device, dtype=torch.int64).contiguous()
         rows, V = lg.shape
         assert t.numel() == rows, "cross_entropy_rows: %d targets for %d rows" % (t.numel(), rows)
-        out = torch.empty(rows, dtype=torch.float32, device=lg.device)
-        _lib.check(_lib.load().mgv_gpt_cross_entropy(self._handle(), _lib.ptr(lg), _lib.ptr(t), rows, V, _lib.ptr(out),
-                                                     _lib.stream_ptr()), "mgv_gpt_cross_entropy")
+        with self._on_device():
+            out = torch.empty(rows, dtype=torch.float32, device=lg.device)
+            _lib.check(_lib.load().mgv_gpt_cross_entropy(self._handle(), _lib.ptr(lg), _lib.ptr(t), rows, V, _lib.ptr(out),
+                                                         _lib.stream_ptr(lg.device)), "mgv_gpt_cross_entropy")
         return out
 
     def last_launches(self):
-        return int(_lib.load().mgv_gpt_last_launches(self._handle()))
+        with self._on_device():
+            return int(_lib.load().mgv_gpt_last_launches(self._handle()))
 
 
 class GPTClass(GPT):
@@ -263,6 +326,8 @@ class Lit_minGPT(_LitBase):
         self.pkeep = pkeep
         self.return_attention = True   # sample() returns the (B,nh,T,T) attention like the reference (:360)
         self.sample_seed = 783435      # Philox key of the device-side sampler; advanced after every sample() call
+        self.record_step_logits = False   # sample() keeps the per-step logits in self.last_step_logits
+        self.last_step_logits = None
         self.datamodule_loader()
         self.forward_shuffle_idx, self.backward_shuffle_idx = self.make_idx(5, 53)
         if getattr(self.args, "reconstruct_spec", "") != "":
@@ -314,8 +379,15 @@ class Lit_minGPT(_LitBase):
         return out
 
     @torch.no_grad()
-    def sample(self, x, c, steps, temperature=1.0, sample=False, top_k=None, callback=lambda k: None):
-        """reference :293-360.  Returns (x (B, t0+steps) int64, att (B, n_head, T, T) fp32 on CPU)."""
+    def sample(self, x, c, steps, temperature=1.0, sample=False, top_k=None, callback=_no_callback):
+        """reference :293-360.  Returns (x (B, t0+steps) int64, att (B, n_head, T, T) fp32 on CPU).
+
+        The whole loop runs on the device (KV cache + CUDA graph) in one libmgv call.  A caller-supplied `callback` is
+        invoked before every step exactly like the reference does (:332), which needs the host in the loop: the tokens
+        are then generated one step per call (each call prefills the KV cache from the tokens so far, i.e. the
+        reference's no-cache schedule) -- same tokens for the same seed, much slower; leave the default for throughput.
+        `self.record_step_logits = True` additionally keeps the logits of every step in `self.last_step_logits`
+        (steps, B, V) for parity checks."""
         block_size = self.transformer.get_block_size()
         assert not self.transformer.training
         if self.pkeep <= 0.0:
@@ -333,24 +405,49 @@ class Lit_minGPT(_LitBase):
             m = 1
         else:
             cls, m = None, 0
-        for k in range(steps):
-            callback(k)                                                       # reference :332
-            assert t0 + k + m <= block_size                                   # reference :336 / :342
         if steps == 0:
             raise UnboundLocalError("local variable 'att' referenced before assignment")   # as the reference (:360)
-        nh = tr.config.n_head
-        Tf = m + t0 + steps - 1
-        out = torch.empty(B, t0 + steps, dtype=torch.int64, device=x.device)
-        att = None
-        if self.return_attention:
-            att = torch.empty(B, nh, Tf, Tf, dtype=torch.float32, device=x.device)
         seed = int(self.sample_seed) & 0xFFFFFFFFFFFFFFFF
         self.sample_seed = (int(self.sample_seed) * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
-        _lib.check(_lib.load().mgv_gpt_generate(
-            tr._handle(), _lib.ptr(x) if t0 > 0 else None, B, t0, None, _lib.ptr(cls), m, int(steps),
-            float(temperature), 1 if sample else 0, int(top_k) if top_k is not None else 0, seed,
-            _lib.ptr(out), _lib.ptr(att), 1, _lib.stream_ptr()), "mgv_gpt_generate")
+        kw = dict(cls=cls, m=m, temperature=temperature, sample=sample, top_k=top_k, seed=seed)
+        self.last_step_logits = None
+        if callback is _no_callback:
+            for k in range(steps):
+                assert t0 + k + m <= block_size                                   # reference :336 / :342
+            out, att, sl = self._generate(x, steps, self.return_attention, self.record_step_logits, **kw)
+        else:
+            out, att, logs = x, None, []
+            for k in range(steps):
+                callback(k)                                                       # reference :332
+                assert out.shape[1] + m <= block_size                             # reference :336 / :342
+                out, att, sl = self._generate(out, 1, self.return_attention and k == steps - 1, self.record_step_logits, **kw)
+                logs.append(sl)
+            sl = torch.cat(logs, 0) if self.record_step_logits else None
+        self.last_step_logits = sl
         return out, (att.detach().cpu() if att is not None else None)
+
+    def _generate(self, x, steps, want_att, want_logits, cls, m, temperature, sample, top_k, seed):
+        """one mgv_gpt_generate call: x (B,t0) -> (B,t0+steps); the Philox counter is (position, row), so a generation split
+        over several calls with the same seed draws the same numbers as a single call"""
+        tr = self.transformer
+        B, t0 = x.shape
+        nh = tr.config.n_head
+        Tf = m + t0 + steps - 1
+        dev = x.device
+        with tr._on_device():
+            out = torch.empty(B, t0 + steps, dtype=torch.int64, device=dev)
+            att = torch.empty(B, nh, Tf, Tf, dtype=torch.float32, device=dev) if want_att else None
+            sl = None
+            L = _lib.load()
+            h = tr._handle()
+            if want_logits:
+                sl = torch.empty(steps, B, tr.config.vocab_size, dtype=torch.float32, device=dev)
+                _lib.check(L.mgv_gpt_set_step_logits(h, _lib.ptr(sl)), "mgv_gpt_set_step_logits")
+            _lib.check(L.mgv_gpt_generate(
+                h, _lib.ptr(x) if t0 > 0 else None, B, t0, None, _lib.ptr(cls), m, int(steps),
+                float(temperature), 1 if sample else 0, int(top_k) if top_k is not None else 0, seed,
+                _lib.ptr(out), _lib.ptr(att), 1, _lib.stream_ptr(dev)), "mgv_gpt_generate")
+        return out, att, sl
 
     # ---------------------------------------------------------------- data plumbing (reference :387-411)
     def get_x(self, batch):

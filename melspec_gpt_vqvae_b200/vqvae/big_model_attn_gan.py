@@ -13,7 +13,9 @@ operation runs in libmgv (hand-written sm_100a CUDA behind the C ABI in include/
 
 The nn.Module tree below exists to own the parameters under the reference's names; the
 packed bf16 copies inside the libmgv handle are derived caches that are refreshed whenever a
-parameter changes (load_state_dict, .to(), in-place updates).  Inference only (the VQVAE
+parameter changes (load_state_dict, .to(), in-place updates that bump the tensor version; edits through
+`.data` need an explicit `refresh_weights()`).  Every libmgv call runs with the parameters' GPU made current
+and on that device's torch stream; the handle is rebuilt when the module moves to another GPU.  Inference only (the VQVAE
 is never trained in the reference repo: README.md:16); no CPU fallback.
 """
 import ctypes
@@ -80,11 +82,16 @@ class VectorQuantizer(nn.Module):
         z = self._check_input(inputs)
         B, C = z.shape[0], z.shape[1]
         HW = z.shape[2] * z.shape[3]
-        idx = torch.empty(B * HW, dtype=torch.int64, device=z.device)
-        L = _lib.load()
-        _lib.check(L.mgv_vq_argmin(_lib.ptr(z), _lib.ptr(cb), B, C, HW, self._num_embeddings, _lib.ptr(idx), None,
-                                   _lib.stream_ptr()), "mgv_vq_argmin")
+        with torch.cuda.device(z.device):
+            idx = torch.empty(B * HW, dtype=torch.int64, device=z.device)
+            _lib.check(_lib.load().mgv_vq_argmin(_lib.ptr(z), _lib.ptr(cb), B, C, HW, self._num_embeddings, _lib.ptr(idx),
+                                                 _lib.ptr(self._dmin(B * HW, z.device)), _lib.stream_ptr(z.device)), "mgv_vq_argmin")
         return idx
+
+    def _dmin(self, n, device):
+        """running-minimum buffer of the multi-pass search (codebooks beyond 128 codes); caller-owned so that concurrent
+        streams / devices never share scratch memory"""
+        return torch.empty(max(n, 1), dtype=torch.float32, device=device) if self._num_embeddings > 128 else None
 
     def _check_input(self, inputs):
         if inputs.dim() != 4 or inputs.shape[1] != self._embedding_dim:
@@ -95,6 +102,8 @@ class VectorQuantizer(nn.Module):
         z = inputs.detach()
         if z.dtype != torch.float32:
             z = z.float()
+        if z.device != self._embedding.weight.device:
+            raise RuntimeError("VectorQuantizer: input is on %s but the codebook is on %s" % (z.device, self._embedding.weight.device))
         return z.contiguous()
 
     @torch.no_grad()
@@ -107,20 +116,22 @@ class VectorQuantizer(nn.Module):
         K = self._num_embeddings
         dev = z.device
         L = _lib.load()
-        st = _lib.stream_ptr()
-        idx = torch.empty(B * HW, dtype=torch.int64, device=dev)
-        _lib.check(L.mgv_vq_argmin(_lib.ptr(z), _lib.ptr(cb), B, C, HW, K, _lib.ptr(idx), None, st), "mgv_vq_argmin")
-        quantized = torch.empty_like(z)
-        encodings = torch.empty(B * HW, K, dtype=torch.float32, device=dev)
-        scalars = torch.zeros(2, dtype=torch.float32, device=dev)
-        if B * HW == 0:     # empty batch: mse / perplexity of nothing (the reference returns nan / 1.0)
-            scalars[0] = float("nan")
-            scalars[1] = 1.0
-            return scalars[0], quantized, (scalars[1], encodings, idx.unsqueeze(1))
-        ws = torch.empty((8 + 4 * K + 7) // 8, dtype=torch.float64, device=dev)
-        _lib.check(L.mgv_vq_finish(_lib.ptr(z), _lib.ptr(cb), _lib.ptr(idx), B, C, HW, K, float(self._commitment_cost),
-                                   _lib.ptr(quantized), _lib.ptr(encodings), ctypes.c_void_p(scalars.data_ptr()),
-                                   ctypes.c_void_p(scalars.data_ptr() + 4), _lib.ptr(ws), st), "mgv_vq_finish")
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            idx = torch.empty(B * HW, dtype=torch.int64, device=dev)
+            _lib.check(L.mgv_vq_argmin(_lib.ptr(z), _lib.ptr(cb), B, C, HW, K, _lib.ptr(idx), _lib.ptr(self._dmin(B * HW, dev)), st),
+                       "mgv_vq_argmin")
+            quantized = torch.empty_like(z)
+            encodings = torch.empty(B * HW, K, dtype=torch.float32, device=dev)
+            scalars = torch.zeros(2, dtype=torch.float32, device=dev)
+            if B * HW == 0:     # empty batch: mse / perplexity of nothing (the reference returns nan / 1.0)
+                scalars[0] = float("nan")
+                scalars[1] = 1.0
+                return scalars[0], quantized, (scalars[1], encodings, idx.unsqueeze(1))
+            ws = torch.empty((8 + 4 * K + 7) // 8, dtype=torch.float64, device=dev)
+            _lib.check(L.mgv_vq_finish(_lib.ptr(z), _lib.ptr(cb), _lib.ptr(idx), B, C, HW, K, float(self._commitment_cost),
+                                       _lib.ptr(quantized), _lib.ptr(encodings), ctypes.c_void_p(scalars.data_ptr()),
+                                       ctypes.c_void_p(scalars.data_ptr() + 4), _lib.ptr(ws), st), "mgv_vq_finish")
         return scalars[0], quantized, (scalars[1], encodings, idx.unsqueeze(1))
 
     @torch.no_grad()
@@ -143,8 +154,9 @@ class VectorQuantizer(nn.Module):
         else:
             out = torch.empty(n, C, dtype=torch.float32, device=idx.device)
             hw = 0
-        _lib.check(L.mgv_vq_gather(_lib.ptr(idx), _lib.ptr(cb), n, C, hw, self._num_embeddings, _lib.ptr(out),
-                                   _lib.ptr(flag), _lib.stream_ptr()), "mgv_vq_gather")
+        with torch.cuda.device(idx.device):
+            _lib.check(L.mgv_vq_gather(_lib.ptr(idx), _lib.ptr(cb), n, C, hw, self._num_embeddings, _lib.ptr(out),
+                                       _lib.ptr(flag), _lib.stream_ptr(idx.device)), "mgv_vq_gather")
         if int(flag.item()) != 0:
             raise RuntimeError("index out of range in get_codebook_entry (num_embeddings=%d)" % self._num_embeddings)
         return out
@@ -312,39 +324,70 @@ class LitVQVAE(_LitBase):
         self.max_adapt_weight = max_adapt_weight
         self._mgv_handle = None
         self._mgv_sig = None
+        self._mgv_dev = None
 
     # ---------------------------------------------------------------- libmgv handle
     def _hot_modules(self):
         return (self._encoder, self._decoder, self._vq_vae, self.quant_conv, self.post_quant_conv)
 
     def _handle(self):
+        """libmgv handle for the device that holds the parameters (call with that device current: `_on_device`)."""
         p = self.quant_conv.weight
         if not p.is_cuda:
             raise RuntimeError("LitVQVAE: parameters are on %s; libmgv has no CPU path -- call .to('cuda')" % p.device)
         L = _lib.load()
         sig = hash(tuple(_params_signature(m) for m in self._hot_modules()))
+        if self._mgv_handle is not None and self._mgv_dev != p.device:
+            self._release_handle()                     # the module moved to another GPU
         if self._mgv_handle is None:
             h = ctypes.c_void_p()
             _lib.check(L.mgv_vqvae_create(int(self.num_embeddings), self.embedding_dim, ctypes.byref(h)), "mgv_vqvae_create")
             self._mgv_handle = h
+            self._mgv_dev = p.device
             self._mgv_sig = None
         if sig != self._mgv_sig:
-            st = _lib.stream_ptr()
+            st = _lib.stream_ptr(p.device)
             for prefix, mod in (("_encoder.", self._encoder), ("_decoder.", self._decoder), ("_vq_vae.", self._vq_vae),
                                 ("quant_conv.", self.quant_conv), ("post_quant_conv.", self.post_quant_conv)):
                 for k, t in mod.state_dict().items():
                     t32 = t.detach().to(torch.float32).contiguous()
                     _lib.check(L.mgv_vqvae_load_weight(self._mgv_handle, (prefix + k).encode(), _lib.ptr(t32),
                                                        t32.numel(), st), "mgv_vqvae_load_weight(%s%s)" % (prefix, k))
-            torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream(p.device).synchronize()
             self._mgv_sig = sig
         return self._mgv_handle
 
+    def _on_device(self):
+        p = self.quant_conv.weight
+        if not p.is_cuda:
+            raise RuntimeError("LitVQVAE: parameters are on %s; libmgv has no CPU path -- call .to('cuda')" % p.device)
+        return torch.cuda.device(p.device)
+
+    def refresh_weights(self):
+        """Re-pack the bf16 weight copies inside libmgv on the next call (needed only after edits through `.data`, which
+        bypass the version counter the automatic check relies on)."""
+        self._mgv_sig = None
+
+    def _release_handle(self):
+        if getattr(self, "_mgv_handle", None) is not None:
+            try:
+                with torch.cuda.device(self._mgv_dev):
+                    _lib.load().mgv_vqvae_destroy(self._mgv_handle)
+            finally:
+                self._mgv_handle = None
+                self._mgv_sig = None
+
+    def __getstate__(self):
+        # the libmgv handle is a process-local cache: drop it so that copy.deepcopy / pickle / torch.save(model) work
+        state = self.__dict__.copy()
+        state["_mgv_handle"] = None
+        state["_mgv_sig"] = None
+        state["_mgv_dev"] = None
+        return state
+
     def __del__(self):
         try:
-            if getattr(self, "_mgv_handle", None) is not None:
-                _lib.load().mgv_vqvae_destroy(self._mgv_handle)
-                self._mgv_handle = None
+            self._release_handle()
         except Exception:
             pass
 
@@ -362,9 +405,10 @@ class LitVQVAE(_LitBase):
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 80, resolution):
             raise RuntimeError("LitVQVAE.encode: expected (B,1,80,%d), got %s" % (resolution, tuple(x.shape)))
         B = x.shape[0]
-        z = torch.empty(B, self.embedding_dim, 5, 53, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().mgv_vqvae_encode(self._handle(), _lib.ptr(x), B, _lib.ptr(z), _lib.stream_ptr()),
-                   "mgv_vqvae_encode")
+        with self._on_device():
+            z = torch.empty(B, self.embedding_dim, 5, 53, dtype=torch.float32, device=x.device)
+            _lib.check(_lib.load().mgv_vqvae_encode(self._handle(), _lib.ptr(x), B, _lib.ptr(z), _lib.stream_ptr(x.device)),
+                       "mgv_vqvae_encode")
         return z
 
     @torch.no_grad()
@@ -374,9 +418,10 @@ class LitVQVAE(_LitBase):
         if q.dim() != 4 or tuple(q.shape[1:]) != (self.embedding_dim, 5, 53):
             raise RuntimeError("LitVQVAE.decode: expected (B,%d,5,53), got %s" % (self.embedding_dim, tuple(q.shape)))
         B = q.shape[0]
-        mel = torch.empty(B, 1, 80, resolution, dtype=torch.float32, device=q.device)
-        _lib.check(_lib.load().mgv_vqvae_decode(self._handle(), _lib.ptr(q), B, _lib.ptr(mel), _lib.stream_ptr()),
-                   "mgv_vqvae_decode")
+        with self._on_device():
+            mel = torch.empty(B, 1, 80, resolution, dtype=torch.float32, device=q.device)
+            _lib.check(_lib.load().mgv_vqvae_decode(self._handle(), _lib.ptr(q), B, _lib.ptr(mel), _lib.stream_ptr(q.device)),
+                       "mgv_vqvae_decode")
         return mel
 
     @torch.no_grad()
@@ -389,9 +434,10 @@ class LitVQVAE(_LitBase):
             raise RuntimeError("LitVQVAE.decode_codes: indices are on %s; libmgv has no CPU path" % idx.device)
         idx = idx.to(torch.int64).reshape(-1, 265).contiguous()
         B = idx.shape[0]
-        mel = torch.empty(B, 1, 80, resolution, dtype=torch.float32, device=idx.device)
-        _lib.check(_lib.load().mgv_vqvae_decode_codes(self._handle(), _lib.ptr(idx), B, _lib.ptr(mel), _lib.stream_ptr()),
-                   "mgv_vqvae_decode_codes")
+        with self._on_device():
+            mel = torch.empty(B, 1, 80, resolution, dtype=torch.float32, device=idx.device)
+            _lib.check(_lib.load().mgv_vqvae_decode_codes(self._handle(), _lib.ptr(idx), B, _lib.ptr(mel),
+                                                          _lib.stream_ptr(idx.device)), "mgv_vqvae_decode_codes")
         return mel
 
     @torch.no_grad()
@@ -406,4 +452,5 @@ class LitVQVAE(_LitBase):
         return loss, x_recon, info
 
     def last_launches(self):
-        return int(_lib.load().mgv_vqvae_last_launches(self._handle()))
+        with self._on_device():
+            return int(_lib.load().mgv_vqvae_last_launches(self._handle()))

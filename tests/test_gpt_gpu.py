@@ -148,10 +148,22 @@ def test_half_prompt_continuation_topk_temperature():
     xs, att = lit.sample(prompt, c, steps=133, temperature=0.7, sample=False, top_k=100)
     assert torch.equal(xs[:, :132], prompt) and xs.shape == (2, 265)
     ref = torch.from_numpy(g2["tokens"].astype(np.int64))
-    agree = float((xs.cpu() == ref).float().mean())
+    xs_cpu = xs.cpu()
+    agree = float((xs_cpu == ref).float().mean())
     print("half-prompt continuation token agreement with the reference: %.4f" % agree)
-    first_div = ((xs.cpu() != ref).float().argmax(1)).tolist()
-    assert agree > 0.5 or min(first_div) > 132     # prefix property: identical until a near-tie flips one step
+    # prefix property: identical to the reference up to the first divergence, and a divergence must be a near-tie of
+    # the reference's own logits at that step (fp32 oracle, teacher-forced on the reference's tokens, same temperature)
+    o_logits, _ = gpt_oracle.lit_forward(sd, gpt_oracle.GPTCfg(**GPT_SMALL), ref, c.cpu())
+    for b in range(2):
+        neq = (xs_cpu[b] != ref[b]).nonzero()
+        if neq.numel() == 0:
+            continue
+        t = int(neq[0])
+        assert t >= 132, "the prompt itself was altered"
+        step = o_logits[b, t] / 0.7
+        chosen_gap = float(step.max() - step[xs_cpu[b, t]])
+        print("half-prompt divergence at b=%d t=%d: our token is %.4f below the reference's maximum" % (b, t, chosen_gap))
+        assert chosen_gap <= 2 * LOGIT_TOL_MAX / 0.7, "real mismatch at step %d of sequence %d" % (t, b)
     with pytest.raises(AssertionError):            # reference: assert x.size(1) + cond_size <= block_size (:336)
         lit.sample(prompt, c, steps=135)
 
