@@ -16,8 +16,11 @@ of the elapsed time.
 
 `--impl reference` times the reference's own algorithm on the host cores instead: the fp32 CPU
 restatement in oracle/ (the reference is pure Python on torch; oracle/ restates it function by
-function and is pinned to the unmodified reference by tests/golden).  It is a bounded sample (the
-full bs=64 no-KV-cache generation takes > 1 h on CPU) extrapolated to the same metric.
+function and is pinned to the unmodified reference by tests/golden).  Each step is a bounded,
+stratified sample of the workload (the full bs=64 no-KV-cache generation takes > 1 h on CPU): the
+sampling step at every (K+W)th context length, so every counted token is computed at its true context.
+At N=1 the default run also times the same reference algorithm with torch eager ON THE GPU
+(`gpu_reference`: fp32 with TF32 off, and autocast bf16) -- the existing-kernels bar on the same box.
 """
 import argparse
 import json
@@ -204,6 +207,8 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if a.warmup < 3 and rank == 0:
+        print("bench.py: --warmup %d raised to 3 (timing rules: at least 3 warm-up steps)" % a.warmup, file=sys.stderr)
     for _ in range(max(a.warmup, 3)):
         step_device()
     # ---- device-resident timing (value) + decode-loop roofline
@@ -231,7 +236,6 @@ def run_ours(a):
     # ---- end-to-end timing through the public API with host buffers
     step_e2e()
     barrier()
-    t0 = time.perf_counter()
     e0.record()
     for _ in range(a.steps):
         xh, melh = step_e2e()
@@ -240,6 +244,24 @@ def run_ours(a):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1), device)
     h2d = c_host.numel() * 8
     d2h = xh.numel() * 8 + melh.numel() * 4
+    # the same call returning what the reference's sample() always returns: the last layer's (B,16,T,T) attention map on the host
+    def step_e2e_att():
+        lit.return_attention = True
+        c = c_host.to(device, non_blocking=True)
+        x, att = lit.sample(x0, c, steps=TOKENS, temperature=1.0, sample=True, top_k=100)
+        mel = lit.decode_to_img(x, zshape)
+        return x.cpu(), mel.cpu(), att
+    step_e2e_att()
+    barrier()
+    n_att = max(1, min(a.steps, 3))
+    e0.record()
+    for _ in range(n_att):
+        xa, mela, atth = step_e2e_att()
+    e1.record()
+    barrier()
+    ms_e2e_att = max_over_ranks(e0.elapsed_time(e1), device) / n_att
+    d2h_att = d2h + atth.numel() * 4
+    lit.return_attention = False
 
     tokens = world * BATCH * TOKENS * a.steps
     value = tokens / (ms_total / 1e3)
@@ -257,7 +279,10 @@ def run_ours(a):
         "generate_ms_per_step": gen_ms / a.steps, "decode_to_mel_ms_per_step": (ms_total - gen_ms) / a.steps,
         "e2e": {"value": tokens / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "Lit_minGPT.sample + decode_to_img, class ids from pinned host memory, tokens + mels copied back; "
-                        "return_attention=False (the (B,16,T,T) attention map the reference also returns is an optional 288 MB logging by-product)"},
+                        "return_attention=False (the (B,16,T,T) attention map the reference also returns is a 288 MB logging by-product: see e2e_with_attention)"},
+        "e2e_with_attention": {"value": world * BATCH * TOKENS / (ms_e2e_att / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                               "d2h_bytes_per_step": d2h_att, "steps": n_att,
+                               "note": "as e2e, with sample() returning the last layer's attention map on the host like the reference (minGPT.py:360)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "gpt decode loop (265 positions, each a CUDA-graph launch of the per-layer kernels)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -271,85 +296,159 @@ def run_ours(a):
         "clocks": clocks,
     }
     if rank == 0:
-        if a.steps <= 4 or True:
-            out["cpu_baseline"] = cpu_baseline(sample_budget_s=a.cpu_budget) if world == 1 else None
+        if world == 1:
+            out["cpu_baseline"] = cpu_baseline(sample_budget_s=a.cpu_budget)
+            out["gpu_reference"] = gpu_reference(device) if not a.no_gpu_reference else None
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_reference_rate(threads, budget_s):
-    """Times the oracle (fp32 CPU restatement of the reference, no KV cache exactly like the reference's
-    sample loop) on a bounded sample and extrapolates to tokens/s for the bs=64 x 265 workload."""
+def reference_positions(offset, stride):
+    """decode positions (= context lengths before the step) visited by one bounded sample"""
+    return list(range(offset, TOKENS, stride))
+
+
+def reference_sample(sd, ocfg, positions, bs, device, gen):
+    """The reference's sampling step (Lit_minGPT.sample, minGPT.py:331-358: FULL forward over the context, no KV
+    cache, temperature, top-k, softmax, multinomial) executed once for every context length in `positions` at batch
+    `bs`.  Every token counted is really computed at its true context length; nothing is extrapolated."""
+    from oracle import gpt_oracle
+    c = torch.randint(0, ocfg.class_size, (bs, 1), generator=gen).to(device)
+    n_tok = 0
+    for n in positions:
+        x = torch.randint(0, ocfg.vocab_size, (bs, n), generator=gen).to(device)
+        gpt_oracle.sample(sd, ocfg, x, c, steps=1, temperature=1.0, sample=True, top_k=100)
+        n_tok += bs
+    return n_tok
+
+
+CPU_BS = 8    # the reference would batch the clips; 8 keeps a sample bounded while giving the CPU GEMMs real batches
+
+
+def cpu_baseline(sample_budget_s=20.0):
+    """cpu_baseline leg of the default run: one stratified sample (every 16th decode position of a 265-token clip at
+    bs=8, i.e. 17 full no-cache sampling steps at their true context lengths) + one VQVAE decode, on all host cores."""
     from melspec_gpt_vqvae_b200 import synthetic
     from oracle import gpt_oracle, vqvae_oracle
+    threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     cfg = synthetic.GPT_VAS
     ocfg = gpt_oracle.GPTCfg(**cfg)
     sd = synthetic.synthetic_gpt_state_dict(cfg, seed=SEED, perturb=False)
     g = torch.Generator().manual_seed(SEED)
-    bs = 8    # the reference would batch the 64 clips; 8 keeps the sample bounded while giving the CPU GEMMs real batches
-    c = torch.randint(0, cfg["class_size"], (bs, 1), generator=g)
-    # the reference recomputes the full forward at every step: cost(n) for context n; sample a few n
-    ctxs = [0, 66, 132, 198, 264]
-    per_ctx = []
-    t_start = time.perf_counter()
-    for n in ctxs:
-        x = torch.randint(0, cfg["vocab_size"], (bs, n), generator=g)
-        t0 = time.perf_counter()
-        xs, _ = gpt_oracle.sample(sd, ocfg, x, c, steps=1, temperature=1.0, sample=True, top_k=100)
-        per_ctx.append((time.perf_counter() - t0) / bs)
-        if time.perf_counter() - t_start > budget_s * 0.6:
-            break
-    # trapezoid over the sampled contexts -> seconds per 265-token clip (generation only)
-    used = ctxs[:len(per_ctx)]
-    gen_s = 0.0
-    for i in range(1, len(used)):
-        gen_s += 0.5 * (per_ctx[i] + per_ctx[i - 1]) * (used[i] - used[i - 1])
-    gen_s += per_ctx[-1] * (TOKENS - 1 - used[-1]) + per_ctx[0]
+    stride = 16 if sample_budget_s >= 15 else 32
+    pos = reference_positions(stride // 2, stride)
+    reference_sample(sd, ocfg, [0, 8], CPU_BS, "cpu", g)          # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    n_tok = reference_sample(sd, ocfg, pos, CPU_BS, "cpu", g)
+    gen_s = time.perf_counter() - t0
     vsd = synthetic.synthetic_vqvae_state_dict(128, 256, seed=SEED, perturb=False, encoder=False)
     codes = torch.randint(0, 128, (1, 265), generator=g)
     t0 = time.perf_counter()
     vqvae_oracle.decode_codes(vsd, codes, 1)
     dec_s = time.perf_counter() - t0
-    per_clip = gen_s + dec_s
-    return TOKENS / per_clip, {"generate_s_per_clip": gen_s, "decode_s_per_clip": dec_s,
-                               "contexts_timed": used, "batch": bs}
+    clips = n_tok / TOKENS                                         # clip-equivalents of generated tokens
+    total_s = gen_s + dec_s * clips
+    return {"value": n_tok / total_s, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "oracle (fp32 torch-CPU restatement of the reference, full forward per token like Lit_minGPT.sample) at bs=%d: "
+                      "the sampling step at every %dth context length of a 265-token clip (%d steps, contexts %d..%d, %.1f s) + the "
+                      "VQVAE decode share of those tokens (%.2f s per clip); every counted token is computed at its true context"
+                      % (CPU_BS, stride, len(pos), pos[0], pos[-1], gen_s, dec_s)}
 
 
-def cpu_baseline(sample_budget_s=20.0):
-    threads = os.cpu_count() or 1
-    rate, info = cpu_reference_rate(threads, sample_budget_s)
-    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "oracle (fp32 torch-CPU restatement of the reference, no KV cache like the reference) at bs=%d: one sampling step at contexts %s "
-                      "integrated over 265 positions + one VQVAE decode; extrapolated to tokens/s for the same per-clip work "
-                      "(generate %.1f s/clip + decode %.1f s/clip)" % (info["batch"], info["contexts_timed"], info["generate_s_per_clip"], info["decode_s_per_clip"])}
+def gpu_reference(device):
+    """The real bar on the same box: the reference's algorithm -- the oracle's functional torch
+    port, full forward per token, no KV cache, ATen / cuBLAS kernels -- on the B200 itself, (a) fp32 with TF32 disabled
+    (the parity configuration) and (b) under torch.autocast(bfloat16).  bs=64, multinomial top-k 100."""
+    from melspec_gpt_vqvae_b200 import synthetic
+    from oracle import gpt_oracle, vqvae_oracle
+    cfg = synthetic.GPT_VAS
+    ocfg = gpt_oracle.GPTCfg(**cfg)
+    sd = {k: v.to(device) for k, v in synthetic.synthetic_gpt_state_dict(cfg, seed=SEED, perturb=False).items()}
+    vsd = {k: v.to(device) for k, v in synthetic.synthetic_vqvae_state_dict(128, 256, seed=SEED, perturb=False, encoder=False).items()}
+    g = torch.Generator().manual_seed(SEED)
+    codes = torch.randint(0, 128, (BATCH, 265), generator=g).to(device)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out = {}
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3, r
+
+    try:
+        for name, stride, ctx in (("autocast_bf16", 1, torch.autocast("cuda", dtype=torch.bfloat16)),
+                                  ("fp32_tf32_off", 8, torch.autocast("cuda", enabled=False))):
+            pos = reference_positions(stride // 2, stride)
+            with ctx:
+                reference_sample(sd, ocfg, [0, 64, 264], BATCH, device, g)       # warm-up (cuBLAS heuristics, allocator)
+                vqvae_oracle.decode_codes(vsd, codes[:8], 8)
+                gen_s, n_tok = timed(lambda: reference_sample(sd, ocfg, pos, BATCH, device, g))
+                dec_s, _ = timed(lambda: [vqvae_oracle.decode_codes(vsd, codes[i:i + 8], 8) for i in range(0, BATCH, 8)])
+            clips = n_tok / TOKENS
+            total_s = gen_s + dec_s * clips / BATCH
+            out[name] = {"value": n_tok / total_s, "unit": UNIT, "generate_s": gen_s, "decode_64_clips_s": dec_s,
+                         "positions": "all 265" if stride == 1 else "every %dth of 265 (%d steps at their true context lengths)" % (stride, len(pos))}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    out["what"] = ("reference algorithm (oracle functional torch port, pinned to the unmodified reference by tests/golden), torch %s eager on "
+                   "this GPU: full forward per generated token (no KV cache), bs=64, + VQVAE decode (batches of 8)" % torch.__version__)
+    del sd, vsd
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(a):
+    """--impl reference: the reference's own CPU algorithm on all host cores.  Step j of the K + W steps runs the sampling
+    step at the context lengths j, j + (K+W), j + 2(K+W), ... of a 265-token clip at bs=8, so the K timed steps together
+    visit K/(K+W) of all decode positions of 8 clips exactly once, each at its true context length (a stratified, bounded,
+    un-extrapolated sample of the workload); the last timed step adds the VQVAE decode of the clip-equivalents generated."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    from melspec_gpt_vqvae_b200 import synthetic
+    from oracle import gpt_oracle, vqvae_oracle
     threads = os.cpu_count() or 1
-    rates = []
-    info = None
-    t0 = time.perf_counter()
-    for i in range(a.warmup + a.steps):
-        r, info = cpu_reference_rate(threads, 12.0)
-        if i >= a.warmup:
-            rates.append(r)
-        if time.perf_counter() - t0 > 150 and rates:
-            break
-    rate = sum(rates) / len(rates)
-    sample = ("oracle port of the reference's CPU path (fp32, torch on %d host threads, full recompute per token as in "
-              "Lit_minGPT.sample): per step one sampling step at contexts %s at bs=%d integrated to a 265-token clip + one VQVAE "
-              "decode; %d timed repeats" % (threads, info["contexts_timed"], info["batch"], len(rates)))
-    out = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": len(rates),
-           "warmup": a.warmup, "ms_per_step": 1e3 * BATCH * TOKENS / rate, "higher_is_better": True, "scaling": "weak",
+    torch.set_num_threads(threads)
+    cfg = synthetic.GPT_VAS
+    ocfg = gpt_oracle.GPTCfg(**cfg)
+    sd = synthetic.synthetic_gpt_state_dict(cfg, seed=SEED, perturb=False)
+    vsd = synthetic.synthetic_vqvae_state_dict(128, 256, seed=SEED, perturb=False, encoder=False)
+    g = torch.Generator().manual_seed(SEED)
+    stride = max(a.steps + a.warmup, 6)
+    n_tok = 0
+    timed_s = 0.0
+    for j in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        n = reference_sample(sd, ocfg, reference_positions(j % stride, stride), CPU_BS, "cpu", g)
+        if j == a.warmup + a.steps - 1:
+            clips = max(1, int(round((n_tok + n) / TOKENS)))
+            vqvae_oracle.decode_codes(vsd, torch.randint(0, 128, (clips, 265), generator=g), clips)
+        dt = time.perf_counter() - t0
+        if j >= a.warmup:
+            n_tok += n
+            timed_s += dt
+    rate = n_tok / timed_s
+    sample = ("oracle port of the reference's CPU path (fp32, torch on %d host threads, full forward per token as in Lit_minGPT.sample, "
+              "bs=%d): each step = the sampling step at every %dth context length of a 265-token clip; the %d timed steps visit %d decode "
+              "positions x %d sequences once each at their true context + the VQVAE decode of the %.1f clip-equivalents generated"
+              % (threads, CPU_BS, stride, a.steps, n_tok // CPU_BS, CPU_BS, n_tok / TOKENS))
+    out = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": 1e3 * timed_s / a.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "clips_per_gpu": BATCH, "tokens_per_clip": TOKENS, "global_clips": BATCH * world},
+           "config": {"workload": WORKLOAD, "clips_per_gpu": BATCH, "tokens_per_clip": TOKENS, "global_clips": BATCH * world,
+                      "sharding": "clips over ranks, no collective", "l2": "per-step working set (605 MB weights + KV) exceeds the 126 MB L2",
+                      "weights": "random init (reference initialisers), seed %d" % SEED},
+           "tokens_per_step": n_tok / a.steps,
            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -363,6 +462,8 @@ def main():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--cpu-budget", dest="cpu_budget", type=float, default=20.0)
+    p.add_argument("--no-gpu-reference", dest="no_gpu_reference", action="store_true",
+                   help="skip the torch-eager reference leg on the GPU (about 15 s)")
     a = p.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -75,7 +75,7 @@ def gpt_forward(sd, cfg, idx, embeddings=None, targets=None):
     t = tok.shape[1]
     assert t <= cfg.block_size, "Cannot forward, model block size is exhausted."           # :178
     x = tok + sd["pos_emb"][:, :t, :]                                                      # :179-180
-    mask = causal_mask(cfg.block_size, cfg.n_unmasked)
+    mask = causal_mask(cfg.block_size, cfg.n_unmasked).to(tok.device)
     att = None
     for i in range(cfg.n_layer):
         x, att = block(sd, i, x, cfg, mask)                                                # :185
