@@ -130,6 +130,34 @@ int mgv_gpt_cross_entropy(mgv_gpt_t* g, const float* logits, const int64_t* targ
 /* number of kernels libmgv launched in the last forward / generate call on this handle */
 int64_t mgv_gpt_last_launches(const mgv_gpt_t* g);
 
+/* ---- minGPT training step (BASELINE config 4).  reference: Lit_minGPT.training_step / shared_step
+ * transformer/minGPT.py:413-422 (teacher-forced logits + mean cross entropy), GPT.forward :168-199 with its three dropouts,
+ * configure_optimizers :618-665 (AdamW, betas (0.9, 0.95), weight decay 0.01 on Linear weights only),
+ * DDP gradient averaging GPT_VAE_train.py:172-174 (done by the host with NCCL between mgv_gpt_train_backward calls).
+ *
+ * The caller owns two flat fp32 device buffers of mgv_gpt_train_numel() elements -- master parameters and gradients -- whose
+ * layout (one 256-byte aligned segment per state_dict tensor, blocks contiguous and in order, q|k|v adjacent) is reported by
+ * mgv_gpt_train_layout.  The handle keeps bf16 / transposed copies for the tcgen05 GEMMs and refreshes them in the optimizer. */
+int64_t mgv_gpt_train_numel(mgv_gpt_t* g);
+/* offset / numel (elements) of state_dict tensor `name` in the flat buffers; *decay = 1 if weight decay applies to it */
+int mgv_gpt_train_layout(mgv_gpt_t* g, const char* name, int64_t* offset, int64_t* numel, int* decay);
+/* attach the flat buffers (the handle must already hold the same weights through mgv_gpt_load_weight) */
+int mgv_gpt_train_bind(mgv_gpt_t* g, float* flat_params, float* flat_grads, mgv_stream_t stream);
+/* forward with dropout (probabilities in [0,1), masks from a counter hash of `seed`): idx (B, t) int64, cls (B) int64 with
+ * m = 1 (or NULL, m = 0), targets (B, m + t) int64; *loss_out (device fp32) = mean cross entropy.  Saves activations. */
+int mgv_gpt_train_forward(mgv_gpt_t* g, const int64_t* idx, int B, int t, const int64_t* cls, int m, const int64_t* targets,
+                          float p_embd, float p_resid, float p_attn, uint64_t seed, float* loss_out, mgv_stream_t stream);
+/* backward of the last forward through blocks layer_hi-1 .. layer_lo.  layer_hi == n_layer first clears the gradient buffer
+ * and runs the head / ln_f part; layer_lo == 0 also runs the embedding backward.  Calling it bucket by bucket lets the host
+ * all-reduce the finished (contiguous) slice of the gradient buffer while the next bucket is computed. */
+int mgv_gpt_train_backward(mgv_gpt_t* g, int layer_hi, int layer_lo, mgv_stream_t stream);
+/* torch.optim.AdamW step on the flat buffers (m, v: fp32 state, same length); gradients are multiplied by grad_scale first */
+int mgv_gpt_train_adamw(mgv_gpt_t* g, float* m, float* v, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        int64_t step, float grad_scale, mgv_stream_t stream);
+/* tests: keep flags (1 / 0) of elements 0..n-1 of dropout stream `stream_id` (1: embedding; 16 + 4l: attention of block l;
+ * 17 + 4l / 18 + 4l: residual dropout after proj / mlp), element index = row-major index of the dropped tensor */
+int mgv_test_dropout_mask(uint64_t seed, unsigned stream_id, float p, int64_t n, unsigned char* out, mgv_stream_t stream);
+
 /* Deterministic decode switch.  The default decode loop reduces split-K partial sums with fp32 atomics whose order depends
  * on CTA timing, so sampled tokens can differ run to run at near-ties (the reference's greedy path is deterministic).
  * on != 0 selects a schedule in which every decode GEMM owns its full K: bit-reproducible, about 2x slower. */

@@ -36,6 +36,13 @@ SIGNATURES = {
     "mgv_gpt_last_launches": (I64, [VP]),
     "mgv_gpt_set_step_logits": (I, [VP, VP]),
     "mgv_gpt_set_deterministic": (I, [VP, I]),
+    "mgv_gpt_train_numel": (I64, [VP]),
+    "mgv_gpt_train_layout": (I, [VP, ctypes.c_char_p, ctypes.POINTER(I64), ctypes.POINTER(I64), ctypes.POINTER(I)]),
+    "mgv_gpt_train_bind": (I, [VP, VP, VP, VP]),
+    "mgv_gpt_train_forward": (I, [VP, VP, I, I, VP, I, VP, F, F, F, ctypes.c_uint64, VP, VP]),
+    "mgv_gpt_train_backward": (I, [VP, I, I, VP]),
+    "mgv_gpt_train_adamw": (I, [VP, VP, VP, F, F, F, F, F, I64, F, VP]),
+    "mgv_test_dropout_mask": (I, [ctypes.c_uint64, ctypes.c_uint, F, I64, VP, VP]),
     "mgv_vqvae_create": (I, [I, I, ctypes.POINTER(VP)]),
     "mgv_vqvae_destroy": (I, [VP]),
     "mgv_vqvae_load_weight": (I, [VP, ctypes.c_char_p, VP, I64, VP]),

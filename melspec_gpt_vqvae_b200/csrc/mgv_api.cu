@@ -3,6 +3,7 @@
 #include <exception>
 #include "gemm_tc.cuh"
 #include "gpt.cuh"
+#include "gpt_train.cuh"
 #include "vq.cuh"
 #include "vqvae.cuh"
 
@@ -212,6 +213,48 @@ int mgv_gpt_cross_entropy(mgv_gpt_t* g, const float* logits, const int64_t* targ
   MGV_API_END
 }
 int64_t mgv_gpt_last_launches(const mgv_gpt_t* g) { return gpt_last_launches(reinterpret_cast<const Gpt*>(g)); }
+// ---- training step (gpt_train.cu)
+int64_t mgv_gpt_train_numel(mgv_gpt_t* g) { return gpt_train_numel(reinterpret_cast<Gpt*>(g)); }
+int mgv_gpt_train_layout(mgv_gpt_t* g, const char* name, int64_t* offset, int64_t* numel, int* decay) {
+  MGV_API_BEGIN
+  long long o = 0, n = 0;
+  const int rc = gpt_train_layout(reinterpret_cast<Gpt*>(g), name, &o, &n, decay);
+  if (rc == MGV_OK) { *offset = o; *numel = n; }
+  return rc;
+  MGV_API_END
+}
+int mgv_gpt_train_bind(mgv_gpt_t* g, float* flat_params, float* flat_grads, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  return gpt_train_bind(reinterpret_cast<Gpt*>(g), flat_params, flat_grads, static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
+int mgv_gpt_train_forward(mgv_gpt_t* g, const int64_t* idx, int B, int t, const int64_t* cls, int m, const int64_t* targets,
+                          float p_embd, float p_resid, float p_attn, uint64_t seed, float* loss_out, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  return gpt_train_forward(reinterpret_cast<Gpt*>(g), reinterpret_cast<const long long*>(idx), B, t,
+                           reinterpret_cast<const long long*>(cls), m, reinterpret_cast<const long long*>(targets), p_embd,
+                           p_resid, p_attn, seed, loss_out, static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
+int mgv_gpt_train_backward(mgv_gpt_t* g, int layer_hi, int layer_lo, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  return gpt_train_backward(reinterpret_cast<Gpt*>(g), layer_hi, layer_lo, static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
+int mgv_gpt_train_adamw(mgv_gpt_t* g, float* m, float* v, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        int64_t step, float grad_scale, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  return gpt_train_adamw(reinterpret_cast<Gpt*>(g), m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                         static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
+int mgv_test_dropout_mask(uint64_t seed, unsigned stream_id, float p, int64_t n, unsigned char* out, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  MGV_TRY(check_device());
+  return train_drop_mask(make_drop(p, seed), stream_id, n, out, static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
+
 int mgv_gpt_set_deterministic(mgv_gpt_t* g, int on) {
   MGV_API_BEGIN
   return gpt_set_deterministic(reinterpret_cast<Gpt*>(g), on);

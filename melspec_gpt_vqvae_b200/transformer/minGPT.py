@@ -228,8 +228,9 @@ class GPT(nn.Module):
 
     def _check_inference(self):
         if self.training and (self.drop.p > 0 or any(b.attn.attn_drop.p > 0 or b.attn.resid_drop.p > 0 for b in self.blocks)):
-            raise NotImplementedError("GPT.forward in training mode with dropout: the B200 path implements the "
-                                      "eval-mode forward only (training is a 'next' row); call .eval()")
+            raise NotImplementedError("GPT.forward in training mode with dropout returns no autograd graph on the B200 path: "
+                                      "use transformer/train_step.py (GPTTrainer.step / Lit_minGPT.training_step) to train, "
+                                      "or call .eval() for inference")
 
     def _forward_impl(self, idx, embeddings, cls):
         self._check_inference()
@@ -472,6 +473,26 @@ class Lit_minGPT(_LitBase):
         x, c = self.get_xc(batch)
         logits, target = self(x, c)
         return self.transformer.cross_entropy_rows(logits.reshape(-1, logits.size(-1)), target.reshape(-1)).mean()
+
+    # ---------------------------------------------------------------- training (reference :413-422, :618-665)
+    def trainer(self):
+        """the GPTTrainer that owns the flat parameter / gradient buffers (created on first use, after .to('cuda'))"""
+        from .train_step import GPTTrainer
+        if getattr(self, "_trainer", None) is None or self._trainer.model._mgv_handle is not self._trainer._bound_handle:
+            self._trainer = GPTTrainer(self.transformer)
+        return self._trainer
+
+    def training_step(self, batch, batch_idx):
+        """Teacher-forced cross entropy like the reference's shared_step -- but forward AND backward run here, in libmgv
+        (there is no autograd graph): the returned loss is a detached device scalar and every `p.grad` is already filled
+        (and all-reduced when torch.distributed is initialised).  Follow it with `optimizer.step()`; under Lightning use
+        manual optimisation."""
+        x, c = self.get_xc(batch)
+        return self.trainer().step(x[:, :-1], c, x)
+
+    def configure_optimizers(self):
+        """AdamW with the reference's decay / no-decay parameter groups (:618-665), fused into one libmgv kernel"""
+        return self.trainer().configure_optimizers(lr=self.args.learning_rate)
 
     def validation_step(self, batch, batch_idx):
         loss = self.shared_step(batch, batch_idx)
