@@ -200,7 +200,20 @@ int gemm(const void* A, const void* Bm, int M, int N, int K, int epi, const floa
   a.max_stages = 3;
   a.A = A; a.B = Bm; a.M = M; a.N = N; a.K = K; a.lda = lda;
   a.epi = epi; a.bias = bias; a.out = out; a.resid = resid;
-  a.bn = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
+  // tile width: the GEMMs of a per-GPU batch of 8 clips give only 30-270 tiles of 128 x 256 on 148 SMs, so pick the width
+  // that minimises (rounds over the SMs) x (time of one tile).  A tile's k-block is bound by the L2 -> shared-memory operand
+  // feed (128 + bn rows of 128 bytes), not by its MMAs, hence the (128 + bn) weight; ties go to the wider tile.
+  const int n_sm = num_sms();
+  const int m_tiles = ceil_div(M, 128);
+  int best_bn = 0;
+  long long best_cost = 0;
+  for (int bn : {256, 128, 64}) {
+    if (N % bn != 0) continue;
+    const long long tiles = static_cast<long long>(m_tiles) * (N / bn);
+    const long long cost = ((tiles + n_sm - 1) / n_sm) * (128 + bn);
+    if (best_bn == 0 || cost < best_cost) { best_bn = bn; best_cost = cost; }
+  }
+  a.bn = best_bn ? best_bn : 32;
   return gemm_bf16_tc(a);
 }
 

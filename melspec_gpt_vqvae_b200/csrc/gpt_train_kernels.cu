@@ -173,18 +173,15 @@ transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int R, int N, long 
 // dbeta += sum_rows dy.  The statistics are recomputed from the saved input row.  A CTA = 8 warps x LNB_ROWS rows each;
 // per-lane partial dgamma / dbeta live in registers, are folded across the warps in shared memory and leave the CTA
 // as one atomicAdd per column.
-constexpr int LNB_ROWS = 4;      // rows per warp
 
 template <int LNB_MAX_V4>        // float4 chunks per lane: C <= 128 * LNB_MAX_V4
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma, int rows,
                      int C, float* __restrict__ dx_io, int accumulate, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta) {
-  extern __shared__ float lnb_smem[];   // [2][C]
+                     float* __restrict__ dbeta, int LNB_ROWS) {
+  extern __shared__ __align__(16) float lnb_smem[];   // [8 warps][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = C / 4;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) lnb_smem[i] = 0.f;
-  __syncthreads();
   float4 dg[LNB_MAX_V4], dbt[LNB_MAX_V4];
 #pragma unroll
   for (int j = 0; j < LNB_MAX_V4; ++j) dg[j] = dbt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -251,21 +248,23 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       }
     }
   }
-  // fold the warps' parameter-gradient partials
+  // fold the warps' parameter-gradient partials: every warp parks its row of 2C partial sums in shared memory, then
+  // thread t adds the 8 warps' values of its columns and issues ONE global atomic per column and CTA
+  float* mine = lnb_smem + static_cast<size_t>(warp) * 2 * C;
 #pragma unroll
   for (int j = 0; j < LNB_MAX_V4; ++j) {
     const int i = lane + 32 * j;
     if (i < nv) {
-      atomicAdd(&lnb_smem[4 * i + 0], dg[j].x); atomicAdd(&lnb_smem[4 * i + 1], dg[j].y);
-      atomicAdd(&lnb_smem[4 * i + 2], dg[j].z); atomicAdd(&lnb_smem[4 * i + 3], dg[j].w);
-      atomicAdd(&lnb_smem[C + 4 * i + 0], dbt[j].x); atomicAdd(&lnb_smem[C + 4 * i + 1], dbt[j].y);
-      atomicAdd(&lnb_smem[C + 4 * i + 2], dbt[j].z); atomicAdd(&lnb_smem[C + 4 * i + 3], dbt[j].w);
+      *reinterpret_cast<float4*>(mine + 4 * i) = dg[j];
+      *reinterpret_cast<float4*>(mine + C + 4 * i) = dbt[j];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(dgamma + i, lnb_smem[i]);
-    atomicAdd(dbeta + i, lnb_smem[C + i]);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += lnb_smem[static_cast<size_t>(w) * 2 * C + i];
+    atomicAdd((i < C ? dgamma : dbeta - C) + i, s);
   }
 }
 
@@ -808,12 +807,22 @@ int train_transpose(const __nv_bfloat16* src, int R, int N, long long ld_src, in
 int train_layernorm_bwd(const float* dy, const float* x, const float* gamma, int rows, int C, float* dx_io, bool accumulate,
                         float* dgamma, float* dbeta, cudaStream_t s) {
   MGV_REQUIRE(C % 4 == 0 && C <= 16 * 128, "layernorm backward: C=%d unsupported", C);
-  const int grid = ceil_div(rows, 8 * LNB_ROWS);
-  const size_t smem = 2 * C * sizeof(float);
+  // rows per warp: enough CTAs to fill the GPU twice over at small batches, fewer column atomics at large ones
+  int rpw = rows / (8 * 2 * num_sms());
+  if (rpw < 1) rpw = 1;
+  if (rpw > 8) rpw = 8;
+  const int grid = ceil_div(rows, 8 * rpw);
+  const size_t smem = static_cast<size_t>(8) * 2 * C * sizeof(float);
   const int acc = accumulate ? 1 : 0;
-  if (C <= 256) layernorm_bwd_kernel<2><<<grid, 256, smem, s>>>(dy, x, gamma, rows, C, dx_io, acc, dgamma, dbeta);
-  else if (C <= 1024) layernorm_bwd_kernel<8><<<grid, 256, smem, s>>>(dy, x, gamma, rows, C, dx_io, acc, dgamma, dbeta);
-  else layernorm_bwd_kernel<16><<<grid, 256, smem, s>>>(dy, x, gamma, rows, C, dx_io, acc, dgamma, dbeta);
+  static unsigned long long attr_mask = 0;
+  if (first_use_on_this_device(attr_mask)) {
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4));
+    MGV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4));
+  }
+  if (C <= 256) layernorm_bwd_kernel<2><<<grid, 256, smem, s>>>(dy, x, gamma, rows, C, dx_io, acc, dgamma, dbeta, rpw);
+  else if (C <= 1024) layernorm_bwd_kernel<8><<<grid, 256, smem, s>>>(dy, x, gamma, rows, C, dx_io, acc, dgamma, dbeta, rpw);
+  else layernorm_bwd_kernel<16><<<grid, 256, smem, s>>>(dy, x, gamma, rows, C, dx_io, acc, dgamma, dbeta, rpw);
   MGV_CHECK_CUDA(cudaGetLastError());
   return MGV_OK;
 }

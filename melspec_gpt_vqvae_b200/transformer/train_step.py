@@ -73,6 +73,8 @@ class GPTTrainer:
         self.layers_per_bucket = max(1, int(layers_per_bucket))
         self.process_group = process_group
         self.grad_scale = 1.0
+        self.allreduce = True            # False: keep the local gradients even when torch.distributed is initialised
+        self.overlap = True              # False: one all-reduce after the whole backward (no overlap; for measurements)
         self._pending = []
         self.seed = 783435
         p0 = model.head.weight
@@ -153,7 +155,8 @@ class GPTTrainer:
         p_attn = float(m.blocks[0].attn.attn_drop.p) if training else 0.0
         self.seed = (self.seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
         self.last_seed = self.seed
-        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1
+        distributed = (self.allreduce and dist.is_available() and dist.is_initialized()
+                       and dist.get_world_size(self.process_group) > 1)
         L = _lib.load()
         self.wait_for_gradients()
         with m._on_device():
@@ -164,10 +167,12 @@ class GPTTrainer:
                                                p_attn, self.seed, _lib.ptr(loss), st), "mgv_gpt_train_forward")
             for hi, lo, f_lo, f_hi in self._buckets():
                 _lib.check(L.mgv_gpt_train_backward(h, hi, lo, st), "mgv_gpt_train_backward")
-                if distributed:
+                if distributed and self.overlap:
                     # NCCL averages this bucket (DDP semantics) on its own stream while the next bucket's backward runs on ours
                     self._pending.append(dist.all_reduce(self.flat_grads[f_lo:f_hi], op=dist.ReduceOp.AVG,
                                                          group=self.process_group, async_op=True))
+        if distributed and not self.overlap:
+            self._pending.append(dist.all_reduce(self.flat_grads, op=dist.ReduceOp.AVG, group=self.process_group, async_op=True))
         if distributed:
             dist.all_reduce(loss, op=dist.ReduceOp.AVG, group=self.process_group)   # logging value (sync_dist)
         return loss
