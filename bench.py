@@ -106,7 +106,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """start of the timed region: nvidia-smi is started before the warm-up (its own start-up takes driver locks for a
+        few hundred ms and would otherwise land inside the first timed steps); only samples after the mark are used."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -118,7 +123,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, ln in self.lines:
+            if ts < t_mark:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -209,13 +217,14 @@ def run_ours(a):
 
     if a.warmup < 3 and rank == 0:
         print("bench.py: --warmup %d raised to 3 (timing rules: at least 3 warm-up steps)" % a.warmup, file=sys.stderr)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(a.warmup, 3)):
         step_device()
     # ---- device-resident timing (value) + decode-loop roofline
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gen_ms = 0.0
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -517,12 +526,13 @@ def run_train(a):
 
     if a.warmup < 3 and rank == 0:
         print("bench.py: --warmup %d raised to 3 (timing rules: at least 3 warm-up steps)" % a.warmup, file=sys.stderr)
-    for _ in range(max(a.warmup, 3)):
-        step_device()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    barrier()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):

@@ -97,6 +97,33 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return MGV_OK;
 }
 
+// fp32 matrix [outer rows][inner] for kind::tf32 operands: 128-byte swizzle = 32 floats per row segment
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                     uint32_t box_inner, uint32_t box_outer) {
+  auto enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return MGV_ERR_CUDA;
+  }
+  MGV_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p not 16-byte aligned", base);
+  MGV_REQUIRE(row_stride_bytes % 16 == 0 && box_inner * 4 == 128, "tensor map (f32): row stride %llu / box %u",
+              static_cast<unsigned long long>(row_stride_bytes), box_inner);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d f32 %llux%llu box %ux%u) failed: CUresult %d",
+              static_cast<unsigned long long>(inner), static_cast<unsigned long long>(outer), box_inner, box_outer,
+              static_cast<int>(r));
+    return MGV_ERR_CUDA;
+  }
+  return MGV_OK;
+}
+
 int make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int C, int W, int H, int N, uint32_t box_c, uint32_t box_w,
                         uint32_t box_h, uint32_t elem_stride) {
   auto enc = get_encode();

@@ -131,6 +131,37 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// kind::tf32 (fp32 words in shared memory, the tensor core reads the upper 19 bits), D = f32.  a_mn / b_mn = 1: that
+// operand is MN-major (its M / N index is the contiguous one) instead of K-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32_f32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4)      // c_format = F32
+         | (2u << 7)    // a_format = TF32
+         | (2u << 10)   // b_format = TF32
+         | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16)
+         | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// MN-major operand with the 128-byte swizzle (cute: Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units):
+// 8 k-rows of 128 bytes (32 fp32 along M/N) form a 1024-byte atom; `lbo_bytes` separates consecutive 128-byte blocks
+// along M/N, `sbo_bytes` consecutive groups of 8 k.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;                      // version 1
+  d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
+  return d;
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -170,6 +201,8 @@ __device__ __forceinline__ bool elect_one() {
 // link-time dependency on libcuda (the build box has no driver).
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner /*K*/, uint64_t outer /*rows*/,
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                     uint32_t box_inner, uint32_t box_outer);
 // NHWC activation tensor: dims (C, W, H, N) innermost first; box (box_c, box_w, box_h, 1);
 // elem_stride applies to W and H (stride-2 convolutions).
 int make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int C, int W, int H, int N, uint32_t box_c,

@@ -132,3 +132,54 @@ def test_vq_large_codebooks_multi_pass(K):
     np.testing.assert_allclose(float(perp), float(r_perp), rtol=1e-4)
     assert enc.shape == (4 * 265, K) and float(enc.sum()) == 4 * 265
     np.testing.assert_array_equal(quant.cpu().numpy(), r_quant)
+
+
+def _argmin_abi(z, cb, want_dmin):
+    """mgv_vq_argmin through ctypes with / without the exact-distance output (the two code paths of the tensor-core
+    prefilter: with dmin every vector's winner is re-evaluated exactly; without it single-candidate vectors are final)."""
+    from melspec_gpt_vqvae_b200 import _lib
+    B, D, H, W = z.shape
+    K = cb.shape[0]
+    zc, cc = z.cuda().contiguous(), cb.cuda().contiguous()
+    idx = torch.full((B * H * W,), -1, dtype=torch.int64, device="cuda")
+    dmin = torch.full((B * H * W,), float("nan"), dtype=torch.float32, device="cuda") if want_dmin else None
+    _lib.check(_lib.load().mgv_vq_argmin(_lib.ptr(zc), _lib.ptr(cc), B, D, H * W, K, _lib.ptr(idx), _lib.ptr(dmin),
+                                         _lib.stream_ptr(zc.device)), "mgv_vq_argmin")
+    torch.cuda.synchronize()
+    return idx.cpu().numpy(), (dmin.cpu().numpy() if want_dmin else None)
+
+
+@pytest.mark.parametrize("name", ["gauss", "all_codes_equal", "zero_vectors", "vectors_on_codes", "near_ties", "k5_d64",
+                                  "large_dynamic_range"])
+def test_vq_prefilter_candidates_are_exact(name):
+    """The TF32 prefilter may only narrow the search: indices AND winning distances must stay bit-identical to the
+    oracle's exhaustive fixed-order evaluation, including inputs built to defeat an approximate search."""
+    g = torch.Generator().manual_seed(len(name))
+    K, D = 128, 256
+    cb = torch.randn(K, D, generator=g) * 0.2
+    z = torch.randn(5, D, 5, 53, generator=g) * 0.2
+    if name == "all_codes_equal":          # 128 candidates per vector: index 0 must win everywhere
+        cb = cb[:1].repeat(K, 1)
+    elif name == "zero_vectors":
+        z[1:3] = 0.0
+    elif name == "vectors_on_codes":       # d = 0 for one code, duplicates of it later in the codebook
+        cb[100] = cb[7]
+        z = cb[torch.randint(0, K, (5 * 265,), generator=g)].reshape(5, 5, 53, D).permute(0, 3, 1, 2).contiguous()
+    elif name == "near_ties":              # codes that differ from each other in the last bits only
+        base = torch.randn(D, generator=g) * 0.2
+        cb = base[None, :] * (1.0 + torch.arange(K)[:, None].float() * 2.0 ** -22)
+    elif name == "k5_d64":
+        K, D = 5, 64
+        cb = torch.randn(K, D, generator=g)
+        z = torch.randn(3, D, 7, 19, generator=g)
+    elif name == "large_dynamic_range":
+        z = z * torch.logspace(-3, 3, 5)[:, None, None, None]
+        cb = cb * torch.logspace(-2, 2, K)[:, None]
+    o_idx, o_dmin = vq_oracle.argmin_exact(z.numpy(), cb.numpy())
+    i1, d1 = _argmin_abi(z, cb, True)
+    i0, _ = _argmin_abi(z, cb, False)
+    assert np.array_equal(i1, o_idx), "exact-distance path: %d rows differ" % int((i1 != o_idx).sum())
+    assert np.array_equal(i0, o_idx), "direct path: %d rows differ" % int((i0 != o_idx).sum())
+    assert np.array_equal(d1.view(np.uint32), o_dmin.view(np.uint32)), "winning distances are not bit-identical"
+    if name == "all_codes_equal":
+        assert (i0 == 0).all()
