@@ -227,6 +227,27 @@ int mgv_test_gemm_fold(int mode, const void* W, const float* src, int Nw, int B,
 int mgv_test_conv3x3(int impl, const void* x_nhwc, const void* w, const float* bias, int n_img, int Hin, int Win,
                      int Cin, int Cout, int stride, void* out_nhwc, const void* resid_nhwc, mgv_stream_t stream);
 
+/* ------------------------------------------------------------------ (5) MelGAN vocoder ---- */
+/* The step after the path's end: mel -> waveform with the MelGAN Generator the callbacks use for audio logging
+ * (vocoder/modules.py:38-80; callers callbacks/GPT_callbacks.py:93-105, callbacks/GPT_VAE_callbacks.py:84-92).  fp32. */
+typedef struct mgv_melgan mgv_melgan_t;
+
+/* Generator(input_size = n_mel_channels, ngf, n_residual_layers)  (vocoder/modules.py:39-77; ratios 8, 8, 2, 2) */
+int mgv_melgan_create(int n_mel_channels, int ngf, int n_residual_layers, mgv_melgan_t** out);
+int mgv_melgan_destroy(mgv_melgan_t* m);
+
+/* state_dict key of the reference Generator with the weight norm applied by the caller (w = g * v / |v|, the norm
+ * over all dimensions but the first: torch.nn.utils.weight_norm, vocoder/modules.py:17-21):
+ *   "model.<i>.weight" | "model.<i>.bias" | "model.<i>.block.{2,4}.{weight,bias}" | "model.<i>.shortcut.{weight,bias}".
+ * Call mgv_melgan_reset_biases before (re)loading a state_dict: a ResnetBlock's shortcut and last convolution run as
+ * one launch whose bias is the sum of both.  src: fp32 device. */
+int mgv_melgan_load_weight(mgv_melgan_t* m, const char* name, const float* src, int64_t numel, mgv_stream_t stream);
+int mgv_melgan_reset_biases(mgv_melgan_t* m, mgv_stream_t stream);
+
+/* Generator.forward (vocoder/modules.py:79-80): mel fp32 (B, n_mel, T), T >= 4 -> wave fp32 (B, 1, 256 * T) in [-1, 1]. */
+int mgv_melgan_forward(mgv_melgan_t* m, const float* mel, int B, int T, float* wave_out, mgv_stream_t stream);
+int64_t mgv_melgan_last_launches(const mgv_melgan_t* m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,12 @@ SIGNATURES = {
     "mgv_vqvae_decode": (I, [VP, VP, I, VP, VP]),
     "mgv_vqvae_encode": (I, [VP, VP, I, VP, VP]),
     "mgv_vqvae_last_launches": (I64, [VP]),
+    "mgv_melgan_create": (I, [I, I, I, ctypes.POINTER(VP)]),
+    "mgv_melgan_destroy": (I, [VP]),
+    "mgv_melgan_load_weight": (I, [VP, ctypes.c_char_p, VP, I64, VP]),
+    "mgv_melgan_reset_biases": (I, [VP, VP]),
+    "mgv_melgan_forward": (I, [VP, VP, I, I, VP, VP]),
+    "mgv_melgan_last_launches": (I64, [VP]),
     "mgv_test_gemm": (I, [I, VP, VP, I, I, I, I, VP, VP, VP, I, I, VP]),
     "mgv_test_gemm_swapab": (I, [I, VP, VP, I, I, I, I, VP, VP, VP, I, I, VP]),
     "mgv_test_gemm_fold": (I, [I, VP, VP, I, I, I, VP, VP, VP, VP, I, I, VP, I, I, VP]),

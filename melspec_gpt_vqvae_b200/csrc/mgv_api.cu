@@ -4,6 +4,7 @@
 #include "gemm_tc.cuh"
 #include "gpt.cuh"
 #include "gpt_train.cuh"
+#include "melgan.cuh"
 #include "vq.cuh"
 #include "vqvae.cuh"
 
@@ -409,5 +410,32 @@ int mgv_test_conv3x3(int impl, const void* x, const void* w, const float* bias, 
   return impl == 0 ? gemm_bf16_tc(a) : gemm_bf16_ref(a);
   MGV_API_END
 }
+
+int mgv_melgan_create(int n_mel_channels, int ngf, int n_residual_layers, mgv_melgan_t** out) {
+  MGV_API_BEGIN
+  return melgan_create(reinterpret_cast<Melgan**>(out), n_mel_channels, ngf, n_residual_layers);
+  MGV_API_END
+}
+int mgv_melgan_destroy(mgv_melgan_t* m) {
+  MGV_API_BEGIN
+  return melgan_destroy(reinterpret_cast<Melgan*>(m));
+  MGV_API_END
+}
+int mgv_melgan_load_weight(mgv_melgan_t* m, const char* name, const float* src, int64_t numel, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  return melgan_load_weight(reinterpret_cast<Melgan*>(m), name, src, numel, static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
+int mgv_melgan_reset_biases(mgv_melgan_t* m, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  return melgan_reset_biases(reinterpret_cast<Melgan*>(m), static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
+int mgv_melgan_forward(mgv_melgan_t* m, const float* mel, int B, int T, float* wave_out, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  return melgan_forward(reinterpret_cast<Melgan*>(m), mel, B, T, wave_out, static_cast<cudaStream_t>(stream));
+  MGV_API_END
+}
+int64_t mgv_melgan_last_launches(const mgv_melgan_t* m) { return melgan_last_launches(reinterpret_cast<const Melgan*>(m)); }
 
 }  // extern "C"

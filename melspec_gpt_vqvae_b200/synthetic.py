@@ -191,3 +191,48 @@ def synthetic_vqvae_state_dict(num_embeddings=128, embedding_dim=256, seed: int 
             t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
         sd[name] = t
     return sd
+
+
+def melgan_param_shapes(n_mel=80, ngf=32, n_residual_layers=3):
+    """state_dict keys / shapes of the reference's MelGAN Generator (vocoder/modules.py:38-77)."""
+    shapes = OrderedDict()
+
+    def conv(prefix, cout, cin, k, transposed=False):
+        first = cin if transposed else cout
+        shapes[prefix + ".bias"] = (cout,)
+        shapes[prefix + ".weight_g"] = (first, 1, 1)
+        shapes[prefix + ".weight_v"] = (cin, cout, k) if transposed else (cout, cin, k)
+
+    mult = 16
+    conv("model.1", mult * ngf, n_mel, 7)
+    i = 2
+    for r in (8, 8, 2, 2):
+        conv("model.%d" % (i + 1), mult * ngf // 2, mult * ngf, 2 * r, transposed=True)
+        for j in range(n_residual_layers):
+            p = "model.%d" % (i + 2 + j)
+            conv(p + ".block.2", mult * ngf // 2, mult * ngf // 2, 3)
+            conv(p + ".block.4", mult * ngf // 2, mult * ngf // 2, 1)
+            conv(p + ".shortcut", mult * ngf // 2, mult * ngf // 2, 1)
+        i += 2 + n_residual_layers
+        mult //= 2
+    conv("model.%d" % (i + 2), 1, ngf, 7)
+    return shapes
+
+
+def synthetic_melgan_state_dict(n_mel=80, ngf=32, n_residual_layers=3, seed: int = 783435):
+    """Random MelGAN weights at a trained-like scale: v ~ U(+-1/sqrt(fan_in)), g = |v| * U(1.4, 2.2) (the effective weight
+    is g v / |v|, so g sets each filter's gain), small biases."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    shapes = melgan_param_shapes(n_mel, ngf, n_residual_layers)
+    for name, shape in shapes.items():
+        if name.endswith("weight_v"):
+            fan_in = shape[1] * shape[2]
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
+    for name, shape in shapes.items():
+        if name.endswith("weight_g"):
+            v = sd[name[:-1] + "v"]
+            sd[name] = v.flatten(1).norm(dim=1).reshape(shape) * (1.4 + 0.8 * torch.rand(shape, generator=g))
+        elif name.endswith("bias"):
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+    return OrderedDict((k, sd[k]) for k in shapes)

@@ -139,3 +139,28 @@ def test_gpt_vae_dropin_state_dict_keys_match_reference():
     masks = {k for k in ref if k.endswith("attn.mask")}      # derived from n_unmasked inside libmgv; optional buffer
     assert ours - masks == ref - masks, (sorted(ours - ref)[:5], sorted(ref - masks - ours)[:5])
     assert m.encoder.transformer.head.weight.shape == (256, 128) and m.decoder.transformer.pos_emb.shape == (1, 266, 128)
+
+
+def test_melgan_dropin_state_dict_keys_and_host_errors():
+    """vocoder/modules.py:Generator drop-in: the reference's state_dict keys / shapes (so best_netG.pt loads), hop length,
+    weight-norm packing, and no CPU path."""
+    from melspec_gpt_vqvae_b200.vocoder.modules import Generator
+    gen = Generator(80, 32, 3)
+    shapes = synthetic.melgan_param_shapes(80, 32, 3)
+    sd = gen.state_dict()
+    assert set(sd) == set(shapes) and all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    assert gen.hop_length == 256
+    # fresh initialisation: g = |v|, i.e. the effective weight equals v (torch.nn.utils.weight_norm at construction)
+    c = gen.model["3"]
+    torch.testing.assert_close(c.effective_weight(), c.weight_v.detach())
+    gen.load_state_dict(synthetic.synthetic_melgan_state_dict(80, 32, 3, seed=3), strict=True)
+    w = c.effective_weight()
+    torch.testing.assert_close(w.flatten(1).norm(dim=1), c.weight_g.detach().flatten())   # |w| = g per input channel
+    with pytest.raises(RuntimeError):
+        gen(torch.zeros(1, 80, 16))          # CPU tensor: no fallback
+    if os.path.isdir("/root/reference/vocoder"):
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        from make_golden_melgan import reference_generator
+        ref = reference_generator(dict(n_mel=80, ngf=32, n_residual_layers=3), seed=3)
+        assert set(ref.state_dict()) == set(sd)

@@ -173,3 +173,15 @@ def test_gpt_vae_oracle_vs_reference_golden(golden_dir):
     sharp["head.weight"] = dsd["head.weight"] * 8.0
     toks, _ = gpt_vae_oracle.decoder_sample(sharp, dcfg, torch.zeros(3, 0, dtype=torch.long), z, steps=24)
     assert np.array_equal(toks.numpy(), g["tokens"][:, :24].astype(np.int64))
+
+
+def test_melgan_oracle_vs_reference_golden(golden_dir):
+    """MelGAN Generator restatement against the unmodified reference class (fixture: make_golden_melgan.py)."""
+    from make_golden_melgan import SMALL, melgan_inputs
+    from oracle import melgan_oracle
+    g = load(golden_dir, "melgan_small.npz")
+    sd = synthetic.synthetic_melgan_state_dict(seed=410, **SMALL)
+    wave = melgan_oracle.generator_forward(sd, melgan_inputs())
+    assert wave.shape == (2, 1, 37 * 256)
+    np.testing.assert_allclose(wave.numpy(), g["wave"], atol=2e-6)
+    assert float(wave.std()) > 0.05          # the fixture exercises the nonlinearity, not a flat line
