@@ -69,7 +69,7 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-NCU_DRAM_OVER_ALGORITHMIC = 1579.7 / 1448.1   # measured DRAM bytes / algorithmic bytes of a decode position (profiles/)
+NCU_DRAM_OVER_ALGORITHMIC = 1557.8 / 1448.1   # measured DRAM bytes / algorithmic bytes of one decode position at context 133 (profiles/r2_decode_dram_ctx133.csv)
 
 
 def decode_algorithmic_bytes(batch, steps, cfg):
@@ -295,9 +295,10 @@ def run_ours(a):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "gpt decode loop (265 positions, each a CUDA-graph launch of the per-layer kernels)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # ncu dram__bytes_read+write over the 195 kernels of one position at context 133
-                     # (profiles/r1_decode_dram_ctx133.csv): 1579.7 MB against 1448.1 MB algorithmic -> x1.091, applied to
-                     # the whole generation (the 32-sequence GEMM tiles read 14 % of the weight bytes a second time)
+                     # ncu dram__bytes_read + write over the 122 kernels of one position at context 133 of the current
+                     # (LayerNorm / GELU folded) chain, profiles/r2_decode_dram_ctx133.csv: 1557.8 MB against 1448.1 MB
+                     # algorithmic -> x1.076, applied to the whole generation (the two 32-sequence CTAs of a feature tile
+                     # fetch part of the weight bytes twice)
                      "traffic": int(gen_bytes * NCU_DRAM_OVER_ALGORITHMIC),
                      "traffic_source": "ncu sample of one decode position (context 133) scaled to the generation",
                      "peak_source": peak_src,

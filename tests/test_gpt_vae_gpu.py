@@ -131,3 +131,31 @@ def test_gpt_vae_medium_config_properties():
     assert z.shape == (4, 1, 1024)
     toks, att = m.decode(z, "beam")
     assert toks.shape == (4, 265) and int(toks.min()) >= 0 and int(toks.max()) < 1024
+
+
+def test_gpt_vae_medium_config_vs_oracle():
+    """BASELINE config 5 at its stated architecture (24 layers, 16 heads, 1024-d, vocab 1024): encoder statistics, decoder
+    logits and the loss against the fp32 oracle on the same seeded weights (B = 2: the oracle runs on the CPU).  Tolerances:
+    the bf16 tolerances of the small-config tests (the 24-layer stack averages the rounding noise, it does not grow)."""
+    from oracle import gpt_vae_oracle
+    cfg = dict(vocab_size=1024, block_size=265, n_layer=24, n_head=16, n_embd=1024)
+    m = _vae(cfg)
+    esd, dsd = vae_state_dicts(cfg)
+    ecfg, dcfg = gpt_vae_oracle.encoder_cfg(**cfg), gpt_vae_oracle.decoder_cfg(**cfg)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(0, 1024, (2, 265), generator=g)
+    z = torch.randn(2, 1, 1024, generator=g) * 0.5
+    o_mean, o_logvar, _ = gpt_vae_oracle.encoder_forward(esd, ecfg, x)
+    mean, logvar, _ = m.encode_stats(x.cuda())
+    e_stats = max(err_stats(mean.cpu(), o_mean)[0], err_stats(logvar.cpu(), o_logvar)[0])
+    o_logits, _ = gpt_vae_oracle.decoder_forward(dsd, dcfg, x, z)
+    logits, _ = m.decoder(x.cuda(), z.cuda())
+    emax, erms = err_stats(logits.cpu(), o_logits)
+    o_rec = gpt_vae_oracle.reconstruct_error(dsd, dcfg, x, z)
+    rec = m.decoder.reconstruct_error(x.cuda(), z.cuda())
+    rerr = float((rec.cpu() - o_rec).abs().max())
+    print("config-5 architecture vs oracle: (mean, logvar) max err %.4f; logits err max %.4f rms %.4f; reconstruction error %s vs %s"
+          % (e_stats, emax, erms, rec.reshape(-1).tolist(), o_rec.reshape(-1).tolist()))
+    assert e_stats <= 3e-2
+    assert emax <= 8e-2 and erms <= 1.5e-2
+    assert rerr <= 1.0          # sum of 265 per-token losses of ~6.9 each
