@@ -318,10 +318,71 @@ def run_ours(a):
         if world == 1:
             out["cpu_baseline"] = cpu_baseline(sample_budget_s=a.cpu_budget)
             out["gpu_reference"] = gpu_reference(device) if not a.no_gpu_reference else None
+            out["other_configs"] = other_configs(lit, cfg, device, peak) if not a.no_other_configs else None
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def other_configs(lit, cfg, device, peak_hbm):
+    """The sub-paths of BASELINE.json's other configs, timed in the same run (N = 1, after the headline measurement, CUDA events):
+    config 2 (extract_codes: encode + quantise 256 mels), the quantiser alone against the HBM roofline (L2 flushed before
+    every call), and the teacher-forced forward of config 1/3's model.  Reported next to the headline, never inside it."""
+    out = {}
+    try:
+        tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        tf_peak = 1343.1
+
+    def timed(fn, n, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    vq = lit.first_stage_model
+    g = torch.Generator().manual_seed(SEED)
+    mel = (torch.rand(256, 1, 80, 848, generator=g) * 2 - 1).to(device)
+    ms = timed(lambda: vq._vq_vae.encoding_indices(vq.encode(mel)), 3)
+    out["config2_extract_codes"] = {"clips_per_s": 256 / ms * 1e3, "ms_per_256_clips": ms, "encoder_tflops": 143.0e9 * 256 / ms / 1e9,
+                                    "tensor_frac": 143.0e9 * 256 / ms / 1e9 / tf_peak,
+                                    "what": "LitVQVAE.encode + VectorQuantizer index search on 256 synthetic mels resident in HBM"}
+    z = vq.encode(mel)
+    del mel
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    ts = []
+    for i in range(12):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        vq._vq_vae.encoding_indices(z)
+        e1.record()
+        e1.synchronize()
+        if i >= 2:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    us = ts[len(ts) // 2]
+    n_vec = z.shape[0] * z.shape[2] * z.shape[3]
+    out["quantiser"] = {"us": us, "vectors": n_vec, "roofline": {"bound": "hbm", "achieved": n_vec * 1032 / us / 1e3, "peak": peak_hbm,
+                                                                 "unit": "GB/s", "frac": n_vec * 1032 / us / 1e3 / peak_hbm},
+                        "what": "mgv_vq_argmin (tcgen05 TF32 prefilter + exact recheck) on (256, 256, 5, 53) fp32, L2 flushed before each call; "
+                                "1032 algorithmic bytes per vector"}
+    del z, flush
+    x = torch.randint(0, cfg["vocab_size"], (BATCH, TOKENS), generator=g).to(device)
+    c = torch.randint(0, cfg["class_size"], (BATCH, 1), generator=g).to(device)
+    ms = timed(lambda: lit(x, c), 5, warm=2)
+    C, L, V = cfg["n_embd"], cfg["n_layer"], cfg["vocab_size"]
+    fl = 2.0 * (L * 12 * C * C + V * C) * BATCH * TOKENS + 4.0 * TOKENS * TOKENS * C * L * BATCH
+    out["teacher_forced_forward"] = {"tokens_per_s": BATCH * TOKENS / ms * 1e3, "ms": ms, "tflops": fl / ms / 1e9, "tensor_frac": fl / ms / 1e9 / tf_peak,
+                                     "what": "Lit_minGPT.forward on 64 x 265 tokens (logits + attention map of the last layer)"}
+    return out
 
 
 def reference_positions(offset, stride):
@@ -603,6 +664,8 @@ def main():
     p.add_argument("--cpu-budget", dest="cpu_budget", type=float, default=20.0)
     p.add_argument("--no-gpu-reference", dest="no_gpu_reference", action="store_true",
                    help="skip the torch-eager reference leg on the GPU (about 15 s)")
+    p.add_argument("--no-other-configs", dest="no_other_configs", action="store_true",
+                   help="skip the sub-path timings of the other BASELINE configs (about 5 s)")
     p.add_argument("--config", default="generate", choices=["generate", "train"],
                    help="generate: BASELINE config 3 (the headline metric, default); train: config 4 training step")
     a = p.parse_args()
