@@ -55,7 +55,11 @@ int mgv_device_check(void);
  * dmin_out: fp32 (B*H*W), the winning distance; optional for num_embeddings <= 128, REQUIRED beyond (the 128-code
  * passes hand the running minimum to each other through it).
  * Distances are fp32, d = (|x|^2 + |e|^2) - 2<x,e>, every sum a sequential fmaf chain over
- * the channel index; first index wins ties (torch.argmin).  oracle/vq_oracle.c restates it. */
+ * the channel index; first index wins ties (torch.argmin).  oracle/vq_oracle.c restates it.
+ * Implementation: a tensor-core (TF32) prefilter narrows every vector to the codes within a proven error margin of the
+ * minimum, the exact chain is evaluated for those only; results are bit-identical to evaluating all K distances.  With
+ * dmin_out == NULL (and K <= 128) vectors with a single candidate skip the exact evaluation.  B*H*W must be below 2^31 - 1024;
+ * the call allocates 16 bytes per vector of stream-ordered scratch (cudaMallocFromPoolAsync on `stream`). */
 int mgv_vq_argmin(const float* z_bchw, const float* codebook, int B, int C, int HW, int K,
                   int64_t* idx_out, float* dmin_out, mgv_stream_t stream);
 
