@@ -11,6 +11,7 @@ buffer (as do their gradients), whose layout is block-contiguous, so that data-p
 contiguous buckets over NCCL / NVLink while the backward of the next bucket is still running.
 """
 import ctypes
+import os
 
 import torch
 
@@ -68,8 +69,10 @@ class GPTTrainer:
         opt.step()
     """
 
-    def __init__(self, model, layers_per_bucket=4, process_group=None):
+    def __init__(self, model, layers_per_bucket=None, process_group=None):
         self.model = model
+        if layers_per_bucket is None:    # blocks per all-reduce bucket (MGV_TRAIN_BUCKET_LAYERS overrides the default)
+            layers_per_bucket = int(os.environ.get("MGV_TRAIN_BUCKET_LAYERS", "4"))
         self.layers_per_bucket = max(1, int(layers_per_bucket))
         self.process_group = process_group
         self.grad_scale = 1.0
