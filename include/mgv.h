@@ -231,6 +231,13 @@ int mgv_test_gemm_fold(int mode, const void* W, const float* src, int Nw, int B,
 int mgv_test_conv3x3(int impl, const void* x_nhwc, const void* w, const float* bias, int n_img, int Hin, int Win,
                      int Cin, int Cout, int stride, void* out_nhwc, const void* resid_nhwc, mgv_stream_t stream);
 
+/* Upsample.forward (vqvae/big_model_attn_gan.py:182-186: nearest 2x, then 3x3 conv pad 1) in the phase form the decoder
+ * uses: four 2x2 convolutions over the low-res NHWC bf16 input with weights pre-summed from w (fp32 OIHW (Cout, Cin, 3, 3)).
+ * impl 0 = tcgen05 implicit GEMM, impl 1 = SIMT reference of the same contract.  out: bf16 (n_img, 2H, 2W, Cout);
+ * scratch: bf16 [16 * Cout * Cin] for the phase weights. */
+int mgv_test_conv_upsample(int impl, const void* x_nhwc, const float* w_oihw, const float* bias, int n_img, int H, int W,
+                           int Cin, int Cout, void* out_nhwc, void* scratch, mgv_stream_t stream);
+
 /* ------------------------------------------------------------------ (5) MelGAN vocoder ---- */
 /* The step after the path's end: mel -> waveform with the MelGAN Generator the callbacks use for audio logging
  * (vocoder/modules.py:38-80; callers callbacks/GPT_callbacks.py:93-105, callbacks/GPT_VAE_callbacks.py:84-92).  fp32. */

@@ -37,6 +37,9 @@ struct KParams {
   // conv
   int a_mode;
   int H, W, Cin, wb, hb, tiles_x, tiles_y, stride, pad;
+  int pad_y, taps_x;              // pad = x padding; filter taps per row (K = taps_y * taps_x * Cin)
+  int oscale, oy, ox;             // output pixel (y, x) is stored at (y * oscale + oy, x * oscale + ox) of an (H*oscale) x (W*oscale) image
+  int gn_tile_base, gn_tiles_img; // GroupNorm slot of tile (img, ty, tx) = img * gn_tiles_img + gn_tile_base + ty * tiles_x + tx
   float* gn_sum;
   int gn_group_ch;
   int evict_first_w;   // L2 evict-first hint on the weight operand
@@ -325,6 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (nkb > p.kb_per_split) nkb = p.kb_per_split;
 
   int m0 = 0, img = 0, x0 = 0, y0 = 0;
+  long long stats_slot = blockIdx.x;
   if (DECODE || p.a_mode == A_PLAIN) {
     m0 = blockIdx.x * BM;
   } else {
@@ -335,6 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     img = t / p.tiles_y;
     x0 = tx * p.wb;
     y0 = ty * p.hb;
+    stats_slot = static_cast<long long>(img) * p.gn_tiles_img + p.gn_tile_base + ty * p.tiles_x + tx;
   }
 
   if (!DECODE && threadIdx.x >= 64) {   // 128 epilogue threads clear their warp's 64 bins
@@ -380,10 +385,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kk = kb0 + kb;
           const int tap = kk / cblocks;
           const int c0 = (kk - tap * cblocks) * BK;
-          const int dy = tap / 3, dx = tap - dy * 3;
+          const int dy = tap / p.taps_x, dx = tap - dy * p.taps_x;
           // input coordinate of the tile's first pixel for this tap
           const int xi = x0 * p.stride + dx - p.pad;
-          const int yi = y0 * p.stride + dy - p.pad;
+          const int yi = y0 * p.stride + dy - p.pad_y;
           tma_load_4d(dst, &tmA, bar, c0, xi, yi, img, hint_a);
         }
       };
@@ -471,7 +476,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ly = r_local / p.wb, lx = r_local - ly * p.wb;
       const int x = x0 + lx, y = y0 + ly;
       row_ok = (x < p.W) && (y < p.H);
-      out_row = ((static_cast<long long>(img) * p.H + y) * p.W + x) * p.ldo;
+      out_row = ((static_cast<long long>(img) * p.H * p.oscale + y * p.oscale + p.oy) * (p.W * p.oscale) + x * p.oscale + p.ox) * p.ldo;
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -532,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int groups_total = p.N / p.gn_group_ch;
       const int g0 = n0 / p.gn_group_ch;
       if (b >= 0 && b < nbins && g0 + (b >> 1) < groups_total)
-        p.gn_sum[(static_cast<long long>(blockIdx.x) * groups_total + g0 + (b >> 1)) * 2 + (b & 1)] =
+        p.gn_sum[(stats_slot * groups_total + g0 + (b >> 1)) * 2 + (b & 1)] =
             (s_bins[b] + s_bins[64 + b]) + (s_bins[128 + b] + s_bins[192 + b]);
     }
   }
@@ -572,6 +577,7 @@ __device__ __forceinline__ PTile decode_tile(const KParams& p, int tile, int n_t
     t.img = r / p.tiles_y;
     t.x0 = tx * p.wb;
     t.y0 = ty * p.hb;
+    t.stats_slot = static_cast<long long>(t.img) * p.gn_tiles_img + p.gn_tile_base + ty * p.tiles_x + tx;
   }
   return t;
 }
@@ -657,7 +663,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int mt = 0; mt < MT; ++mt) {
           t[mt] = sub_tile(tile, mt);
           xb[mt] = t[mt].x0 * p.stride - p.pad;
-          yb[mt] = t[mt].y0 * p.stride - p.pad;
+          yb[mt] = t[mt].y0 * p.stride - p.pad_y;
         }
         int cb = 0, dx = 0, dy = 0;          // conv: channel block and filter tap of the next k-block
         for (int kb = 0; kb < nkb; kb += KSUB) {
@@ -676,7 +682,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
             if (p.a_mode != A_PLAIN && ++cb == cblocks) {
               cb = 0;
-              if (++dx == 3) {
+              if (++dx == p.taps_x) {
                 dx = 0;
                 ++dy;
               }
@@ -757,7 +763,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int ly = r_local / p.wb, lx = r_local - ly * p.wb;
         const int x = t.x0 + lx, y = t.y0 + ly;
         row_ok = tile_ok && (x < p.W) && (y < p.H);
-        out_row = ((static_cast<long long>(t.img) * p.H + y) * p.W + x) * p.ldo;
+        out_row = ((static_cast<long long>(t.img) * p.H * p.oscale + y * p.oscale + p.oy) * (p.W * p.oscale) + x * p.oscale + p.ox) * p.ldo;
       }
       if (p.gn_sum != nullptr) {   // [MT][4 quarters][64] bins; cleared after the previous flush barrier
         s_bins[et] = 0.f;
@@ -815,9 +821,10 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* __restrict__ A, const __nv_
     const int x = static_cast<int>(m % p.W);
     const int y = static_cast<int>((m / p.W) % p.H);
     const int img = static_cast<int>(m / (static_cast<long long>(p.W) * p.H));
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3, dx = tap % 3;
-      const int xi = x * p.stride + dx - p.pad, yi = y * p.stride + dy - p.pad;
+    const int ntaps = p.K / p.Cin;
+    for (int tap = 0; tap < ntaps; ++tap) {
+      const int dy = tap / p.taps_x, dx = tap % p.taps_x;
+      const int xi = x * p.stride + dx - p.pad, yi = y * p.stride + dy - p.pad_y;
       if (xi < 0 || yi < 0 || xi >= Win || yi >= Hin) continue;
       const __nv_bfloat16* a = A + ((static_cast<long long>(img) * Hin + yi) * Win + xi) * p.Cin;
       const __nv_bfloat16* b = B + static_cast<long long>(n) * p.K + tap * p.Cin;
@@ -825,7 +832,12 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* __restrict__ A, const __nv_
     }
   }
   if (p.bias) acc += p.transpose_out ? p.bias[m] : p.bias[n];
-  const long long o = p.transpose_out ? static_cast<long long>(n) * p.ldo + m : m * p.ldo + n;
+  long long o = p.transpose_out ? static_cast<long long>(n) * p.ldo + m : m * p.ldo + n;
+  if (p.a_mode != A_PLAIN) {
+    const int x = static_cast<int>(m % p.W), y = static_cast<int>((m / p.W) % p.H);
+    const long long img = m / (static_cast<long long>(p.W) * p.H);
+    o = ((img * p.H * p.oscale + y * p.oscale + p.oy) * (p.W * p.oscale) + x * p.oscale + p.ox) * p.ldo + n;
+  }
   switch (p.epi) {
     case EPI_BF16: static_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(acc); break;
     case EPI_BF16_GELU: static_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(gelu_erf(acc)); break;
@@ -870,7 +882,9 @@ int fill_params(const GemmArgs& a, KParams& p) {
   }
   if (a.a_mode == A_CONV3x3) {
     MGV_REQUIRE(a.n_img > 0 && a.H > 0 && a.W > 0 && a.Cin > 0 && a.Cin % BK == 0, "conv: bad geometry");
-    MGV_REQUIRE(a.K == 9 * a.Cin, "conv: K=%d != 9*Cin", a.K);
+    MGV_REQUIRE(a.taps_x >= 1 && a.taps_x <= 3 && a.K % (a.taps_x * a.Cin) == 0, "conv: K=%d is not taps_y * %d * Cin", a.K, a.taps_x);
+    MGV_REQUIRE(a.out_scale >= 1 && a.out_oy >= 0 && a.out_oy < a.out_scale && a.out_ox >= 0 && a.out_ox < a.out_scale, "conv: output placement");
+    MGV_REQUIRE(a.out_scale == 1 || a.resid == nullptr, "conv: strided output placement has no residual form");
     MGV_REQUIRE(a.M == a.n_img * a.H * a.W, "conv: M mismatch");
     MGV_REQUIRE(a.stride == 1 || a.stride == 2, "conv: stride");
     p.H = a.H;
@@ -878,12 +892,17 @@ int fill_params(const GemmArgs& a, KParams& p) {
     p.Cin = a.Cin;
     p.stride = a.stride;
     p.pad = a.pad;
-    int wb = 16;
-    while (wb < 128 && wb < a.W) wb *= 2;
-    p.wb = wb;
-    p.hb = BM / wb;
+    p.pad_y = a.pad_y >= 0 ? a.pad_y : a.pad;
+    p.taps_x = a.taps_x;
+    p.oscale = a.out_scale;
+    p.oy = a.out_oy;
+    p.ox = a.out_ox;
+    p.wb = conv_tile_width(a.H, a.W);
+    p.hb = BM / p.wb;
     p.tiles_x = ceil_div(a.W, p.wb);
     p.tiles_y = ceil_div(a.H, p.hb);
+    p.gn_tiles_img = a.gn_tiles_img > 0 ? a.gn_tiles_img : p.tiles_x * p.tiles_y;
+    p.gn_tile_base = a.gn_tile_base;
   }
   return MGV_OK;
 }

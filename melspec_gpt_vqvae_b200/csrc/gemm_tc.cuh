@@ -7,6 +7,7 @@
 //     the image border = the convolution's zero padding; element stride 2 = stride-2 conv).
 // D[M,N] = A[M,K] * B[N,K]^T, A/B bf16 K-major, fp32 accumulation in TMEM.
 #pragma once
+#include <stdlib.h>
 #include "mgv_sm100.cuh"
 
 namespace mgv {
@@ -44,6 +45,12 @@ struct GemmArgs {
   // conv geometry (A_CONV3x3): output HxW, input Hin x Win, stride 1 or 2
   int a_mode = A_PLAIN;
   int n_img = 0, H = 0, W = 0, Hin = 0, Win = 0, Cin = 0, stride = 1, pad = 1;
+  // generalisations used by the phase form of Upsample (nearest 2x + 3x3 conv == four 2x2 convs on the low-res tensor):
+  // taps per filter row (K = taps_y * taps_x * Cin), a y padding different from `pad` (-1: same), and a strided output
+  // placement: pixel (y, x) of the H x W grid goes to (y*out_scale + out_oy, x*out_scale + out_ox) of an
+  // (H*out_scale) x (W*out_scale) output image.  GroupNorm partial sums of tile (img, ty, tx) go to slot
+  // img * gn_tiles_img + gn_tile_base + ty * tiles_x + tx (0: tiles per image of this launch, base 0).
+  int taps_x = 3, pad_y = -1, out_scale = 1, out_oy = 0, out_ox = 0, gn_tiles_img = 0, gn_tile_base = 0;
   // GroupNorm statistics fused into the epilogue (conv): per (image, channel-group of
   // `gn_group_ch` output channels) sum and sum of squares of the bf16-rounded outputs.
   // Every CTA stores (no atomics -> deterministic) its partial sums to
@@ -62,6 +69,30 @@ struct GemmArgs {
 };
 
 int gemm_bf16_tc(const GemmArgs& a);
+
+// Width (in output pixels) of a conv M tile: the 128 rows of a tile are a wb x (128 / wb) pixel rectangle, and the choice
+// among 128 / 64 / 32 / 16 that covers the H x W image with the fewest padded pixels wins (ties: the wider one).  E.g.
+// 80 x 848 is covered exactly by 16 x 8 rectangles while 128 x 1 strips pad every row to 896 (5.7 % wasted MMA work),
+// and 40 x 424 pads to 512 with strips (20.8 %) but to 432 with 16 x 8 rectangles (1.9 %).
+inline int conv_tile_width(int H, int W) {
+  static const bool legacy = getenv("MGV_CONV_WB_LEGACY") != nullptr;   // first version: the widest strip that fits
+  if (legacy) {
+    int wb = 16;
+    while (wb < 128 && wb < W) wb *= 2;
+    return wb;
+  }
+  int best = 128;
+  long long best_area = -1;
+  for (int wb = 128; wb >= 16; wb /= 2) {
+    const int hb = 128 / wb;
+    const long long area = static_cast<long long>((W + wb - 1) / wb) * wb * ((H + hb - 1) / hb) * hb;
+    if (best_area < 0 || area < best_area) {
+      best_area = area;
+      best = wb;
+    }
+  }
+  return best;
+}
 
 // Decode-step GEMM without split-K (gemm_decode_fullk.cu): a CTA = 128 weight rows x 32 sequences x all of K;
 // epi in {EPI_BF16_GELU, EPI_F32, EPI_F32_RESID}; W bf16 [Nw, K], X bf16 [B, K], K % 256 == 0.

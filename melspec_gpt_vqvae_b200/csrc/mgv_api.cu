@@ -2,6 +2,7 @@
 #include <cudaTypedefs.h>
 #include <exception>
 #include "gemm_tc.cuh"
+#include "vqvae_kernels.cuh"
 #include "gpt.cuh"
 #include "gpt_train.cuh"
 #include "melgan.cuh"
@@ -408,6 +409,33 @@ int mgv_test_conv3x3(int impl, const void* x, const void* w, const float* bias, 
   a.bn = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
   a.stream = static_cast<cudaStream_t>(stream);
   return impl == 0 ? gemm_bf16_tc(a) : gemm_bf16_ref(a);
+  MGV_API_END
+}
+
+int mgv_test_conv_upsample(int impl, const void* x, const float* w_oihw, const float* bias, int n_img, int H, int W, int Cin,
+                           int Cout, void* out, void* scratch, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  MGV_TRY(check_device());
+  MGV_REQUIRE(x && w_oihw && out && scratch, "conv_upsample: null");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(scratch);
+  MGV_TRY(vqvae_upsample_phase_weights(w_oihw, Cout, Cin, wp, s));
+  for (int ph = 0; ph < 4; ++ph) {
+    GemmArgs a;
+    a.a_mode = A_CONV3x3;
+    a.A = x; a.B = wp + static_cast<size_t>(ph) * Cout * 4 * Cin;
+    a.n_img = n_img; a.Hin = H; a.Win = W; a.Cin = Cin; a.stride = 1;
+    a.H = H; a.W = W;
+    a.taps_x = 2; a.pad = 1 - (ph & 1); a.pad_y = 1 - (ph >> 1);
+    a.out_scale = 2; a.out_oy = ph >> 1; a.out_ox = ph & 1;
+    a.M = n_img * H * W; a.N = Cout; a.K = 4 * Cin;
+    a.epi = EPI_BF16;
+    a.bias = bias; a.out = out;
+    a.bn = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
+    a.stream = s;
+    MGV_TRY(impl == 0 ? gemm_bf16_tc(a) : gemm_bf16_ref(a));
+  }
+  return MGV_OK;
   MGV_API_END
 }
 

@@ -27,6 +27,7 @@ constexpr int MAX_TILES_PER_IMAGE = 80 * 7;   // 80x848 output: 7 x-tiles of 128
 
 struct Conv {   // 3x3 or 1x1 convolution, weights [Cout][taps][Cin] bf16
   __nv_bfloat16* w = nullptr;
+  __nv_bfloat16* w_up = nullptr;   // Upsample convs only: phase weights [4][Cout][2x2 taps][Cin] (vqvae_upsample_phase_weights)
   float* b = nullptr;
   int cin = 0, cout = 0, k = 0;
 };
@@ -63,13 +64,14 @@ __global__ void repack_convout_kernel(const float* __restrict__ in, int C, float
 }  // namespace
 
 // how a state_dict tensor is stored in the handle
-enum SlotKind { SLOT_F32, SLOT_CONV3, SLOT_CONV1, SLOT_QKV_W, SLOT_QKV_B, SLOT_CONVOUT_W, SLOT_IGNORE };
+enum SlotKind { SLOT_F32, SLOT_CONV3, SLOT_CONV3_UP, SLOT_CONV1, SLOT_QKV_W, SLOT_QKV_B, SLOT_CONVOUT_W, SLOT_IGNORE };
 struct Slot {
   SlotKind kind;
   void* dst;
   long long numel;
   int a, b;       // conv: cout, cin ; qkv: part, C
   bool loaded;
+  void* dst2 = nullptr;   // SLOT_CONV3_UP: the phase weights
 };
 
 struct Vqvae {
@@ -205,7 +207,14 @@ void register_all(Vqvae* v) {
       block_in = block_out;
       if (lvl == NUM_RES - 1) reg_attn(v, fmt("_decoder.up.%d.attn.%d", lvl, b), &v->dec_up_attn[b], block_in);
     }
-    if (lvl != 0) reg_conv(v, fmt("_decoder.up.%d.upsample.conv", lvl), &v->dec_upsample[lvl], block_in, block_in, 3);
+    if (lvl != 0) {
+      Conv* uc = &v->dec_upsample[lvl];
+      reg_conv(v, fmt("_decoder.up.%d.upsample.conv", lvl), uc, block_in, block_in, 3);
+      uc->w_up = dalloc<__nv_bfloat16>(v, static_cast<size_t>(16) * block_in * block_in);
+      Slot& sl = v->slots[fmt("_decoder.up.%d.upsample.conv.weight", lvl)];
+      sl.kind = SLOT_CONV3_UP;
+      sl.dst2 = uc->w_up;
+    }
   }
   reg_gn(v, "_decoder.norm_out", &v->dec_norm_out, block_in);
   v->dec_conv_out_w = dalloc<float>(v, 9 * block_in);
@@ -289,11 +298,43 @@ int conv3(Ctx& c, const Conv& w, const __nv_bfloat16* x, int Hin, int Win, int s
   if (stats_out && unfused) return stats_of(c, out, a.H * a.W, w.cout, stats_out);
   if (stats_out) {
     // tiles per image of the conv kernel's grid (see fill_params in gemm_tc.cu)
-    int wb = 16;
-    while (wb < 128 && wb < a.W) wb *= 2;
+    const int wb = conv_tile_width(a.H, a.W);
     const int tiles = ceil_div(a.W, wb) * ceil_div(a.H, 128 / wb);
     MGV_REQUIRE(tiles <= MAX_TILES_PER_IMAGE, "conv3: %d tiles per image exceed the statistics scratch", tiles);
     MGV_TRY(vqvae_gn_finalize(c.v->gn_part, c.B, tiles, static_cast<float>(a.H) * a.W * (w.cout / 32), stats_out, c.s));
+    c.v->launches++;
+  }
+  return MGV_OK;
+}
+
+// Upsample.forward (:182-186): nearest 2x + 3x3 conv, computed as four 2x2 convolutions over the LOW-res input (one per
+// output phase (py, px), weights pre-summed at load time): 16 instead of 36 multiply-adds per input pixel and channel
+// pair, and the 4x larger upsampled tensor is never written or read.  x: B x H x W x cin; out: B x 2H x 2W x cout.
+int conv_up(Ctx& c, const Conv& w, const __nv_bfloat16* x, int H, int W, __nv_bfloat16* out, float* stats_out) {
+  const int wb = conv_tile_width(H, W);
+  const int tiles = ceil_div(W, wb) * ceil_div(H, 128 / wb);   // per image and phase (fill_params in gemm_tc.cu)
+  MGV_REQUIRE(4 * tiles <= MAX_TILES_PER_IMAGE, "conv_up: %d tiles per image exceed the statistics scratch", 4 * tiles);
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    GemmArgs a;
+    a.a_mode = A_CONV3x3;
+    a.A = x; a.B = w.w_up + static_cast<size_t>(ph) * w.cout * 4 * w.cin;
+    a.n_img = c.B; a.Hin = H; a.Win = W; a.Cin = w.cin; a.stride = 1;
+    a.H = H; a.W = W;
+    a.taps_x = 2; a.pad = 1 - px; a.pad_y = 1 - py;
+    a.out_scale = 2; a.out_oy = py; a.out_ox = px;
+    a.M = c.B * H * W; a.N = w.cout; a.K = 4 * w.cin;
+    a.epi = EPI_BF16;
+    a.bias = w.b; a.out = out;
+    a.bn = (w.cout % 256 == 0 && !getenv("MGV_NO_BN256")) ? 256 : 128;
+    a.max_stages = conv_stages();
+    if (stats_out) { a.gn_sum = c.v->gn_part; a.gn_group_ch = w.cout / 32; a.gn_tiles_img = 4 * tiles; a.gn_tile_base = ph * tiles; }
+    a.stream = c.s;
+    c.v->launches++;
+    MGV_TRY(gemm_bf16_tc(a));
+  }
+  if (stats_out) {
+    MGV_TRY(vqvae_gn_finalize(c.v->gn_part, c.B, 4 * tiles, 4.0f * H * W * (w.cout / 32), stats_out, c.s));
     c.v->launches++;
   }
   return MGV_OK;
@@ -418,7 +459,10 @@ int vqvae_load_weight(Vqvae* v, const char* name, const float* src, long long nu
       MGV_CHECK_CUDA(cudaMemcpyAsync(sl.dst, src, numel * 4, cudaMemcpyDeviceToDevice, s));
       break;
     case SLOT_CONV3:
+    case SLOT_CONV3_UP:
       MGV_TRY(vqvae_repack_conv_weight(src, sl.a, sl.b, 3, 3, static_cast<__nv_bfloat16*>(sl.dst), s));
+      if (sl.kind == SLOT_CONV3_UP)
+        MGV_TRY(vqvae_upsample_phase_weights(src, sl.a, sl.b, static_cast<__nv_bfloat16*>(sl.dst2), s));
       break;
     case SLOT_CONV1:
     case SLOT_QKV_W:
@@ -500,12 +544,18 @@ int vqvae_decode(Vqvae* v, const long long* idx, const float* quant_bchw, int B,
     }
     if (lvl != 0) {
       const Conv& uc = v->dec_upsample[lvl];
-      MGV_TRY(vqvae_upsample2x(h, B, H, W, uc.cin, ta, s));
-      H *= 2; W *= 2;
       st2 = c.new_stats();
-      MGV_TRY(conv3(c, uc, ta, H, W, 1, o, nullptr, st2));
+      static const bool phase_form = getenv("MGV_UPSAMPLE_EXPLICIT") == nullptr;
+      if (phase_form) {
+        MGV_TRY(conv_up(c, uc, h, H, W, o, st2));
+        H *= 2; W *= 2;
+      } else {   // the literal form: materialise the upsampled tensor, then the 3x3 conv (kept for A/B measurements)
+        MGV_TRY(vqvae_upsample2x(h, B, H, W, uc.cin, ta, s));
+        H *= 2; W *= 2;
+        MGV_TRY(conv3(c, uc, ta, H, W, 1, o, nullptr, st2));
+        v->launches++;
+      }
       std::swap(h, o); st = st2;
-      v->launches++;
     }
   }
   MGV_REQUIRE(c.next_slot <= v->gn_slots, "vqvae_decode: statistics slots exhausted");

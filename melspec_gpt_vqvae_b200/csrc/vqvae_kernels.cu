@@ -562,9 +562,43 @@ conv_in_1ch_kernel(const float* __restrict__ mel, const float* __restrict__ w, c
   }
 }
 
+// Upsample (nearest 2x, then 3x3 conv pad 1: big_model_attn_gan.py:182-186) as four 2x2 convolutions over the LOW-res
+// tensor: output pixel (2y+py, 2x+px) only ever sees input rows {y-1, y} (py = 0) or {y, y+1} (py = 1), likewise in x, so
+// the filter rows / columns that land on the same input pixel are summed once here (fp32, then one rounding to bf16).
+// src fp32 OIHW (Cout, Cin, 3, 3) -> dst bf16 [phase = py*2+px][Cout][tap = ty*2+tx][Cin]
+__global__ void upsample_phase_weights_kernel(const float* __restrict__ src, int Cout, int Cin, __nv_bfloat16* __restrict__ dst) {
+  const long long total = 16LL * Cout * Cin;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cin);
+    long long r = i / Cin;
+    const int tap = static_cast<int>(r & 3);
+    r >>= 2;
+    const int o = static_cast<int>(r % Cout);
+    const int ph = static_cast<int>(r / Cout);
+    const int py = ph >> 1, px = ph & 1, ty = tap >> 1, tx = tap & 1;
+    // filter rows that fall on input row (y + ty - (1 - py)): py=0: {0} | {1,2};  py=1: {0,1} | {2}
+    const int ky0 = (py == 0) ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2);
+    const int ky1 = (py == 0) ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+    const int kx0 = (px == 0) ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2);
+    const int kx1 = (px == 0) ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+    const float* w = src + (static_cast<long long>(o) * Cin + c) * 9;
+    float acc = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) acc += w[ky * 3 + kx];
+    dst[i] = __float2bfloat16(acc);
+  }
+}
+
 }  // namespace
 
 // ====================================================================== host wrappers
+int vqvae_upsample_phase_weights(const float* src, int Cout, int Cin, __nv_bfloat16* dst, cudaStream_t s) {
+  upsample_phase_weights_kernel<<<grid_for(16LL * Cout * Cin, 256), 256, 0, s>>>(src, Cout, Cin, dst);
+  MGV_CHECK_CUDA(cudaGetLastError());
+  return MGV_OK;
+}
+
 int vqvae_repack_conv_weight(const float* src, int Cout, int Cin, int KH, int KW, __nv_bfloat16* dst, cudaStream_t s) {
   const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
   repack_conv_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, Cout, Cin, KH * KW, dst);

@@ -8,6 +8,9 @@ namespace mgv {
 
 // conv weight (Cout, Cin, KH, KW) fp32 -> [Cout][KH*KW][Cin] bf16 (K-major rows for the GEMM)
 int vqvae_repack_conv_weight(const float* src, int Cout, int Cin, int KH, int KW, __nv_bfloat16* dst, cudaStream_t s);
+// phase weights of Upsample (nearest 2x + 3x3 conv) as four 2x2 convs on the low-res tensor:
+// src fp32 OIHW (Cout, Cin, 3, 3) -> dst bf16 [py*2+px][Cout][ty*2+tx][Cin]
+int vqvae_upsample_phase_weights(const float* src, int Cout, int Cin, __nv_bfloat16* dst, cudaStream_t s);
 
 // table[k][:] = codebook[k] @ Wpq^T + bpq   (get_codebook_entry :56-71 fused with post_quant_conv :611)
 int vqvae_build_gather_table(const float* codebook, const float* wpq /*(Cout,Cin) fp32*/, const float* bpq, int K,

@@ -26,7 +26,7 @@ import torch.nn as nn
 from torch.nn import functional as F
 
 from .. import _lib
-from ..vqvae.big_model_attn_gan import LitVQVAE, _params_signature
+from ..vqvae.big_model_attn_gan import LitVQVAE, _params_signature, _SigCacheMixin
 
 try:
     import pytorch_lightning as pl
@@ -100,7 +100,7 @@ class Block(nn.Module):
         raise NotImplementedError("Block: " + _HOT_PATH_ONLY)
 
 
-class GPT(nn.Module):
+class GPT(_SigCacheMixin, nn.Module):
     """ the full GPT language model, with a context size of block_size (reference :121-199) """
 
     def __init__(self, args, embd_pdrop=0., resid_pdrop=0., attn_pdrop=0., n_unmasked=0, last_linear=None,
@@ -126,6 +126,7 @@ class GPT(nn.Module):
         self._mgv_sig = None
         self._mgv_dev = None
         self._deterministic = False
+        self._sig_cache_reset()
         logger.info("number of parameters: %e", sum(p.numel() for p in self.parameters()))
 
     def get_block_size(self):
@@ -165,7 +166,7 @@ class GPT(nn.Module):
             self._mgv_sig = None
             if self._deterministic:
                 _lib.check(L.mgv_gpt_set_deterministic(h, 1), "mgv_gpt_set_deterministic")
-        sig = _params_signature(self)
+        sig = _params_signature(self, self)
         if sig != self._mgv_sig:
             st = _lib.stream_ptr(p.device)
             for k, t in self.state_dict().items():
@@ -188,8 +189,9 @@ class GPT(nn.Module):
     def refresh_weights(self):
         """Re-pack the bf16 weight copies inside libmgv on the next call.  Needed only after edits that bypass autograd's
         version counter (`p.data.copy_()`, `p.data.mul_()` ...): load_state_dict, .to() and ordinary in-place ops are
-        detected automatically."""
+        detected automatically.  Also needed after re-binding an attribute to a new nn.Parameter object."""
         self._mgv_sig = None
+        self._sig_cache_reset()
 
     @property
     def deterministic(self):
@@ -218,6 +220,7 @@ class GPT(nn.Module):
         state["_mgv_handle"] = None
         state["_mgv_sig"] = None
         state["_mgv_dev"] = None
+        state["_mgv_sig_tensors"] = {}
         return state
 
     def __del__(self):

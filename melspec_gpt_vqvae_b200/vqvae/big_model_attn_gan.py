@@ -47,12 +47,38 @@ _HOT_PATH_ONLY = ("this submodule only owns parameters; the computation runs fus
                   "LitVQVAE.encode / LitVQVAE.decode / VectorQuantizer.forward instead")
 
 
-def _params_signature(module):
-    """Changes whenever any parameter/buffer is replaced or modified in place."""
-    sig = []
-    for t in list(module.parameters()) + list(module.buffers()):
-        sig.append((t.data_ptr(), t._version, t.device.index if t.is_cuda else -1))
-    return hash(tuple(sig))
+def _params_signature(module, owner=None):
+    """Changes whenever any parameter/buffer is modified in place or moved (data pointer, version counter, device).
+
+    Walking `module.parameters()` costs ~1.3 ms for the VQVAE (GPU idle meanwhile), so the tensor list is cached on
+    `owner` (a `_SigCacheMixin` module) and rebuilt after `_apply` (.to / .cuda / .half ...), `load_state_dict` and
+    `refresh_weights`; re-binding an attribute to a NEW nn.Parameter object needs `refresh_weights()`."""
+    ts = None
+    cache = owner.__dict__.get("_mgv_sig_tensors") if owner is not None else None
+    if cache is not None:
+        ts = cache.get(id(module))
+    if ts is None:
+        ts = list(module.parameters()) + list(module.buffers())
+        if cache is not None:
+            cache[id(module)] = ts
+    return hash(tuple([(t.data_ptr(), t._version, t.device.index if t.is_cuda else -1) for t in ts]))
+
+
+class _SigCacheMixin:
+    """Invalidation points of the cached tensor list `_params_signature` uses."""
+
+    def _sig_cache_reset(self):
+        self.__dict__["_mgv_sig_tensors"] = {}
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._sig_cache_reset()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._sig_cache_reset()
+        return out
 
 
 class VectorQuantizer(nn.Module):
@@ -296,7 +322,7 @@ class NLayerDiscriminator(_Container):
         self.main = nn.Sequential(*layers)
 
 
-class LitVQVAE(_LitBase):
+class LitVQVAE(_SigCacheMixin, _LitBase):
     """reference :538-614.  encode / decode / _vq_vae are the hot path; the GAN training methods
     (loss, training_step, configure_optimizers ...) are out of scope and not provided."""
 
@@ -325,6 +351,7 @@ class LitVQVAE(_LitBase):
         self._mgv_handle = None
         self._mgv_sig = None
         self._mgv_dev = None
+        self._sig_cache_reset()
 
     # ---------------------------------------------------------------- libmgv handle
     def _hot_modules(self):
@@ -336,7 +363,7 @@ class LitVQVAE(_LitBase):
         if not p.is_cuda:
             raise RuntimeError("LitVQVAE: parameters are on %s; libmgv has no CPU path -- call .to('cuda')" % p.device)
         L = _lib.load()
-        sig = hash(tuple(_params_signature(m) for m in self._hot_modules()))
+        sig = hash(tuple(_params_signature(m, self) for m in self._hot_modules()))
         if self._mgv_handle is not None and self._mgv_dev != p.device:
             self._release_handle()                     # the module moved to another GPU
         if self._mgv_handle is None:
@@ -365,8 +392,9 @@ class LitVQVAE(_LitBase):
 
     def refresh_weights(self):
         """Re-pack the bf16 weight copies inside libmgv on the next call (needed only after edits through `.data`, which
-        bypass the version counter the automatic check relies on)."""
+        bypass the version counter the automatic check relies on, or after re-binding an attribute to a new nn.Parameter)."""
         self._mgv_sig = None
+        self._sig_cache_reset()
 
     def _release_handle(self):
         if getattr(self, "_mgv_handle", None) is not None:
@@ -383,6 +411,7 @@ class LitVQVAE(_LitBase):
         state["_mgv_handle"] = None
         state["_mgv_sig"] = None
         state["_mgv_dev"] = None
+        state["_mgv_sig_tensors"] = {}
         return state
 
     def __del__(self):

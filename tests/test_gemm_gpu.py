@@ -162,6 +162,31 @@ def test_conv3x3_vs_torch(n, H, W, Cin, Cout, stride, resid):
     assert (out.float() - ref).abs().max().item() <= (1.0 / 64) * scale
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("n,H,W,Cin,Cout", [
+    (2, 5, 53, 512, 512), (3, 10, 106, 256, 256), (1, 20, 212, 256, 256), (2, 40, 424, 128, 128), (1, 7, 19, 64, 96),
+])
+def test_conv_upsample_phase_form_vs_torch(impl, n, H, W, Cin, Cout):
+    """Upsample.forward (reference big_model_attn_gan.py:182-186): nearest 2x + conv3x3 pad 1, computed as four 2x2
+    convolutions on the low-res tensor with pre-summed weights, against torch on the materialised upsampled tensor."""
+    if impl == 1 and H * W > 3000:
+        pytest.skip("SIMT reference: small cases only")
+    torch.manual_seed(H * W + Cin)
+    x = (torch.randn(n, H, W, Cin, device="cuda") * 0.5).bfloat16()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05
+    bias = torch.randn(Cout, device="cuda")
+    up = torch.nn.functional.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = torch.nn.functional.conv2d(up, w, bias, padding=1).permute(0, 2, 3, 1).contiguous()
+    out = torch.full(ref.shape, float("nan"), device="cuda", dtype=torch.bfloat16)
+    scratch = torch.empty(16 * Cout * Cin, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.load().mgv_test_conv_upsample(impl, _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), n, H, W, Cin, Cout,
+                                                  _lib.ptr(out), _lib.ptr(scratch), S0))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), "every output pixel of every phase must be written"
+    scale = ref.abs().max().item()
+    assert (out.float() - ref).abs().max().item() <= (1.0 / 64) * scale
+
+
 def test_gemm_rejects_bad_shapes():
     A = torch.zeros(4, 60, device="cuda", dtype=torch.bfloat16)
     B = torch.zeros(32, 60, device="cuda", dtype=torch.bfloat16)
