@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libmgv.so")
 
-SOURCES = ["mgv_api.cu", "vq.cu", "gemm_tc.cu", "gemm_decode_fold.cu", "gemm_decode_fullk.cu", "gpt_kernels.cu", "gpt.cu", "gpt_train_kernels.cu", "gpt_train.cu", "vqvae_kernels.cu", "vqvae.cu", "melgan.cu"]
+SOURCES = ["mgv_api.cu", "vq.cu", "gemm_tc.cu", "gemm_decode_fold.cu", "gemm_decode_fullk.cu", "gpt_kernels.cu", "attn_prefill_tc.cu", "gpt.cu", "gpt_train_kernels.cu", "gpt_train.cu", "vqvae_kernels.cu", "vqvae.cu", "melgan.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
