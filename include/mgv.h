@@ -231,6 +231,11 @@ int mgv_test_gemm_fold(int mode, const void* W, const float* src, int Nw, int B,
 int mgv_test_conv3x3(int impl, const void* x_nhwc, const void* w, const float* bias, int n_img, int Hin, int Win,
                      int Cin, int Cout, int stride, void* out_nhwc, const void* resid_nhwc, mgv_stream_t stream);
 
+/* Causal self-attention of a whole sequence (CausalSelfAttention.forward transformer/minGPT.py:70-92, head dim 64):
+ * qkv bf16 [B*T, 3*nh*64] = [q | k | v] -> y bf16 [B*T, nh*64].  impl 0 = tcgen05 kernel, impl 1 = mma.sync kernel.
+ * trace (impl 0, optional): 48 int64 clock stamps of one CTA. */
+int mgv_test_attention_prefill(int impl, const void* qkv, int B, int T, int nh, void* y, int64_t* trace, mgv_stream_t stream);
+
 /* Upsample.forward (vqvae/big_model_attn_gan.py:182-186: nearest 2x, then 3x3 conv pad 1) in the phase form the decoder
  * uses: four 2x2 convolutions over the low-res NHWC bf16 input with weights pre-summed from w (fp32 OIHW (Cout, Cin, 3, 3)).
  * impl 0 = tcgen05 implicit GEMM, impl 1 = SIMT reference of the same contract.  out: bf16 (n_img, 2H, 2W, Cout);

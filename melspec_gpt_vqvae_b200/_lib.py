@@ -60,6 +60,7 @@ SIGNATURES = {
     "mgv_test_gemm_swapab": (I, [I, VP, VP, I, I, I, I, VP, VP, VP, I, I, VP]),
     "mgv_test_gemm_fold": (I, [I, VP, VP, I, I, I, VP, VP, VP, VP, I, I, VP, I, I, VP]),
     "mgv_test_conv3x3": (I, [I, VP, VP, VP, I, I, I, I, I, I, VP, VP, VP]),
+    "mgv_test_attention_prefill": (I, [I, VP, I, I, I, VP, VP, VP]),
     "mgv_test_conv_upsample": (I, [I, VP, VP, VP, I, I, I, I, I, VP, VP, VP]),
 }
 

@@ -9,12 +9,16 @@
 //   TMEM           S_i = Q_i K^T for all tiles side by side (16 + 144 + 272 fp32 columns) + 64 columns for O_0;
 //                  O_i (i >= 1) reuses the first 64 columns of S_i once the softmax has consumed it.
 // S:  tcgen05.mma kind::f16, A = Q tile (K-major), B = K rows (K-major), N split into chunks of <= 256 keys.
-// softmax: 4 warps, thread = query row (TMEM lane); exact two-pass form (row maximum, then exp2 / sum) over the causal
-//          prefix of the row only (32-column chunks beyond a warp's last key are written as zeros, never loaded);
+// softmax: 8 warps, two per TMEM lane quarter (a thread = one query row x every other 32-column chunk; partial row maxima
+//          and sums are exchanged through shared memory); exact two-pass form (row maximum, then exp2 / sum) over the
+//          causal prefix of the row only (chunks beyond a warp's last key are written as zeros, never loaded; chunks
+//          entirely below the diagonal skip the mask arithmetic);
 //          P goes to shared memory as bf16 in the K-major 128-byte-swizzled layout of an MMA A operand -- into the
 //          Q | K region, which is dead once every S MMA has completed.
 // O = P V: A = P (K-major), B = V in the layout TMA delivered it: rows = keys, 64 contiguous head dims = an MN-major
 //          operand (descriptor form verified by tools/probes/bf16_mn_probe.cu: SBO = 8 keys x 128 B, K step = 2048 B).
+// Order: the LAST tile (the long one) first -- its softmax overlaps the issue of the other tiles' MMAs (one thread issues
+// every tcgen05.mma at ~120 cycles apiece) and the kernel's tail is the short tile.
 // No [T, T] tensor reaches HBM.  The kernel covers the plain causal mask without the attention-map output and without
 // the KV-cache fill; gpt_attention_prefill keeps the mma.sync kernel for those cases.
 #include <stdlib.h>
@@ -27,7 +31,7 @@ using namespace sm100;
 
 namespace {
 
-constexpr int AT_THREADS = 192;     // warp 0: TMA + MMA issue, warp 1: TMEM allocation, warps 2..5: softmax / epilogue
+constexpr int AT_THREADS = 320;     // warp 0: TMA + MMA issue, warp 1: TMEM allocation, warps 2..9: softmax / epilogue
 constexpr int AT_TILE_BYTES = 128 * 128;   // 128 rows x 64 bf16
 constexpr int AT_MAX_TILES = 3;
 
@@ -35,15 +39,25 @@ struct AttnTcParams {
   int T, nh, C;
   int n_tiles;
   int row0[AT_MAX_TILES], nrows[AT_MAX_TILES], kpad[AT_MAX_TILES], scol[AT_MAX_TILES], ocol[AT_MAX_TILES];
-  int nkb;            // 128-key boxes of K / V
+  int kmax;           // key rows of K / V in shared memory (= kpad of the last tile)
+  int q0_small;       // tile 0 has at most 16 rows: one 16-row box instead of a 128-row one
+  int qoff[AT_MAX_TILES], koff;   // byte offsets of the Q tiles and of K in shared memory
+  int pk_bytes;       // bytes of the Q | K region (>= the P tiles of the last tile, which reuse it)
+  int p1_bytes;       // second P region (tiles at odd distance from the last one), so that consecutive tiles never share one
   int tmem_cols;      // power of two
   __nv_bfloat16* y;   // [B*T, C]
+  long long* trace;   // optional (diagnostics): clock64 stamps of CTA 0, [16] per recording thread
 };
 
 // kind::f16, A = bf16 K-major, B = bf16 K-major (b_mn = 0) or MN-major (b_mn = 1), D = f32
 __host__ __device__ constexpr uint32_t at_idesc(int M, int N, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {   // one FMNMX3 on sm_100
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -52,36 +66,77 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p) {
+attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm16, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // [n_tiles] x 16 KB   } reused for P after the S MMAs
-  uint8_t* sK = sQ + p.n_tiles * AT_TILE_BYTES;         // [nkb] x 16 KB       }
-  const int pk_tiles = (p.n_tiles + p.nkb > (p.kpad[p.n_tiles - 1] + 63) / 64) ? p.n_tiles + p.nkb
-                                                                               : (p.kpad[p.n_tiles - 1] + 63) / 64;
-  uint8_t* sV = smem + pk_tiles * AT_TILE_BYTES;        // [nkb] x 16 KB: row = key, 128 B = 64 head dims
+  uint8_t* sQ = smem;                                   // Q tiles, last tile first (a short tile 0 takes 2 KB) } reused for P
+  uint8_t* sK = smem + p.koff;                          // [kmax] x 128 B                                       } after the S MMAs
+  uint8_t* sV = smem + p.pk_bytes;                      // [kmax] x 128 B: row = key, 128 B = 64 head dims
   uint8_t* sP = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.nkb * AT_TILE_BYTES);
-  uint64_t* bar_qk = bars;
-  uint64_t* bar_v = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_p = bars + 3;                           // [3] P_i written
-  uint64_t* bar_o = bars + 6;                           // [3] O_i complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sP1 = sV + p.kmax * 128;
+  float* s_m = reinterpret_cast<float*>(sP1 + p.p1_bytes);    // [2][128] partial row maxima of the two column halves
+  float* s_l = s_m + 256;                                     // [2][128] partial row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_l + 256);
+  uint64_t* bar_qk = bars;                              // Q of the last tile + K landed
+  uint64_t* bar_q = bars + 1;                           // the other Q tiles landed
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;                           // [0] S of the last tile complete, [1] every S complete
+  uint64_t* bar_p = bars + 5;                           // [3] P_i written
+  uint64_t* bar_o = bars + 8;                           // [3] O_i complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.nh, h = blockIdx.x - b * p.nh;
+  // diagnostics: thread 0 (TMA / MMA issuer) -> slots 0..15, thread 96 (warp 3: quarter 3, half 0) -> 16..31,
+  // thread 224 (warp 7: quarter 3, half 1) -> 32..47
+  const bool tr = p.trace != nullptr && blockIdx.x == gridDim.x / 2 &&
+                  (threadIdx.x == 0 || threadIdx.x == 96 || threadIdx.x == 224);
+  long long* trp = p.trace + (threadIdx.x == 0 ? 0 : (threadIdx.x == 96 ? 16 : 32));
+  int tri = 0;
+#define AT_STAMP() do { if (tr && tri < 16) trp[tri++] = clock64(); } while (0)
+  AT_STAMP();
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tm);
+    prefetch_tensormap(&tm16);
     mbar_init(bar_qk, 1);
+    mbar_init(bar_q, 1);
     mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
+    mbar_init(&bar_s[0], 1);
+    mbar_init(&bar_s[1], 1);
     for (int i = 0; i < AT_MAX_TILES; ++i) {
-      mbar_init(&bar_p[i], 128);
+      mbar_init(&bar_p[i], AT_THREADS - 64);
       mbar_init(&bar_o[i], 1);
     }
     fence_barrier_init();
+    // The loads are issued before the TMEM allocation is awaited (shapes small enough for two CTAs per SM: the second
+    // one sits in tcgen05.alloc until TMEM is free, with its operands already landing).
+    // ---- loads.  The tiles are processed LAST TILE FIRST (it is the long one: its softmax then overlaps the issue of
+    // the remaining MMAs, and the tail of the kernel is the short tile), so its Q rows and K go first, on their own barrier.
+    // 128-row boxes, then 16-row boxes for the remainder (T = 265: 272 key rows = 2 x 128 + 16; Q tile 0 = 16 rows)
+    const int kfull = p.kmax / 128, krem = (p.kmax - kfull * 128) / 16;
+    const int last = p.n_tiles - 1;
+    const uint32_t q0_bytes = p.q0_small ? 16 * 128 : AT_TILE_BYTES;
+    mbar_arrive_expect_tx(bar_qk, (last == 0 ? q0_bytes : AT_TILE_BYTES) + static_cast<uint32_t>(p.kmax) * 128);
+    tma_load_4d(sQ + p.qoff[last], (last == 0 && p.q0_small) ? &tm16 : &tm, bar_qk, h * GPT_HEAD_DIM, p.row0[last], b, 0,
+                kEvictFirst);
+    for (int j = 0; j < kfull; ++j)
+      tma_load_4d(sK + j * AT_TILE_BYTES, &tm, bar_qk, p.C + h * GPT_HEAD_DIM, j * 128, b, 0, kEvictFirst);
+    for (int j = 0; j < krem; ++j)
+      tma_load_4d(sK + (kfull * 128 + j * 16) * 128, &tm16, bar_qk, p.C + h * GPT_HEAD_DIM, kfull * 128 + j * 16, b, 0,
+                  kEvictFirst);
+    if (last > 0) {
+      mbar_arrive_expect_tx(bar_q, q0_bytes + static_cast<uint32_t>(last - 1) * AT_TILE_BYTES);
+      for (int i = last - 1; i >= 0; --i)
+        tma_load_4d(sQ + p.qoff[i], (i == 0 && p.q0_small) ? &tm16 : &tm, bar_q, h * GPT_HEAD_DIM, p.row0[i], b, 0,
+                    kEvictFirst);
+    }
+    mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(p.kmax) * 128);
+    for (int j = 0; j < kfull; ++j)
+      tma_load_4d(sV + j * AT_TILE_BYTES, &tm, bar_v, 2 * p.C + h * GPT_HEAD_DIM, j * 128, b, 0, kEvictFirst);
+    for (int j = 0; j < krem; ++j)
+      tma_load_4d(sV + (kfull * 128 + j * 16) * 128, &tm16, bar_v, 2 * p.C + h * GPT_HEAD_DIM, kfull * 128 + j * 16, b, 0,
+                  kEvictFirst);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
@@ -91,24 +146,18 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  AT_STAMP();
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- loads: Q tiles + K boxes on one barrier, V boxes on another (V is needed only after the first softmax)
-      mbar_arrive_expect_tx(bar_qk, static_cast<uint32_t>(p.n_tiles + p.nkb) * AT_TILE_BYTES);
-      for (int i = 0; i < p.n_tiles; ++i)
-        tma_load_4d(sQ + i * AT_TILE_BYTES, &tm, bar_qk, h * GPT_HEAD_DIM, p.row0[i], b, 0, kEvictFirst);
-      for (int j = 0; j < p.nkb; ++j)
-        tma_load_4d(sK + j * AT_TILE_BYTES, &tm, bar_qk, p.C + h * GPT_HEAD_DIM, j * 128, b, 0, kEvictFirst);
-      mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(p.nkb) * AT_TILE_BYTES);
-      for (int j = 0; j < p.nkb; ++j)
-        tma_load_4d(sV + j * AT_TILE_BYTES, &tm, bar_v, 2 * p.C + h * GPT_HEAD_DIM, j * 128, b, 0, kEvictFirst);
+      const int last = p.n_tiles - 1;
+      AT_STAMP();
 
-      // ---- S_i = Q_i K^T (all tiles back to back; N in chunks of <= 256 keys, 4 K steps of 16 head dims)
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      for (int i = 0; i < p.n_tiles; ++i) {
-        const uint64_t da = make_smem_desc_sw128(smem_u32(sQ + i * AT_TILE_BYTES));
+      // ---- S_i = Q_i K^T, last tile first (N in chunks of <= 256 keys, 4 K steps of 16 head dims).  Rows of a short
+      // tile 0 beyond its 16-row box are whatever shared memory held: they only reach accumulator rows that no one
+      // reads unmasked.
+      auto issue_s = [&](int i) {
+        const uint64_t da = make_smem_desc_sw128(smem_u32(sQ + p.qoff[i]));
         for (int n0 = 0; n0 < p.kpad[i]; n0 += 256) {
           const int n = (p.kpad[i] - n0 < 256) ? p.kpad[i] - n0 : 256;
           const uint64_t db = make_smem_desc_sw128(smem_u32(sK) + n0 * 128);
@@ -117,99 +166,146 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParam
           for (int k = 0; k < GPT_HEAD_DIM / 16; ++k)
             umma_bf16(tmem_base + p.scol[i] + n0, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
         }
+      };
+      mbar_wait(bar_qk, 0);
+      AT_STAMP();
+      tc_fence_after();
+      issue_s(last);
+      tc_commit(&bar_s[0]);
+      AT_STAMP();
+      if (last > 0) {
+        mbar_wait(bar_q, 0);
+        tc_fence_after();
+        for (int i = last - 1; i >= 0; --i) issue_s(i);
       }
-      tc_commit(bar_s);
+      tc_commit(&bar_s[1]);
+      AT_STAMP();
 
       // ---- O_i = P_i V as soon as the softmax warps have written P_i
       mbar_wait(bar_v, 0);
       const uint32_t idesc_pv = at_idesc(128, GPT_HEAD_DIM, 1);
-      for (int i = 0; i < p.n_tiles; ++i) {
+      for (int i = last; i >= 0; --i) {
         mbar_wait(&bar_p[i], 0);
+        AT_STAMP();
         tc_fence_after();
         const int ksteps = p.kpad[i] / 16;
         for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t da = make_smem_desc_sw128(smem_u32(sP) + (ks >> 2) * AT_TILE_BYTES + (ks & 3) * 32);
+          const uint64_t da = make_smem_desc_sw128(smem_u32(((last - i) & 1) ? sP1 : sP) + (ks >> 2) * AT_TILE_BYTES + (ks & 3) * 32);
           const uint64_t db = make_smem_desc_mn_sw128(smem_u32(sV) + ks * 2048, 8192, 1024);
           umma_bf16(tmem_base + p.ocol[i], da, db, idesc_pv, ks != 0 ? 1u : 0u);
         }
         tc_commit(&bar_o[i]);
+        AT_STAMP();
       }
     }
   } else if (warp >= 2) {
-    // ---- softmax + epilogue: TMEM lane quarter = warp & 3, thread = one query row of the tile
+    // ---- softmax + epilogue: TMEM lane quarter = warp & 3; the two warps of a quarter take alternate 32-column chunks
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int rl = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     // 1/sqrt(d) (minGPT.py:81) folded with log2(e): probabilities are exp2(s' - max')
     const float scale2 = 1.4426950408889634f * 0.125f;
-    mbar_wait(bar_s, 0);
+    mbar_wait(&bar_s[0], 0);
     tc_fence_after();
+    AT_STAMP();
 
-    float l_prev = 0.f;
+    float lsum[AT_MAX_TILES] = {0.f, 0.f, 0.f};
+    // normalise and store this thread's half (32 head dims) of output row rl of tile i
     auto epilogue = [&](int i, float l) {
       mbar_wait(&bar_o[i], 0);
       tc_fence_after();
       const bool ok = rl < p.nrows[i];
       const float inv = ok ? 1.0f / l : 0.f;
-      __nv_bfloat16* dst = p.y + (static_cast<long long>(b) * p.T + p.row0[i] + rl) * p.C + h * GPT_HEAD_DIM;
+      __nv_bfloat16* dst = p.y + (static_cast<long long>(b) * p.T + p.row0[i] + rl) * p.C + h * GPT_HEAD_DIM + half * 32;
+      uint32_t r[32];
+      tmem_ld_32x32(lane_base + p.ocol[i] + half * 32, r);
+      tmem_ld_wait();
+      if (ok) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(lane_base + p.ocol[i] + c * 32, r);
-        tmem_ld_wait();
-        if (ok) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 q;
-            q.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-            q.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-            q.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-            q.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) = q;
-          }
+        for (int j = 0; j < 4; ++j) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+          q.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+          q.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+          q.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + j * 8) = q;
         }
       }
     };
 
-    for (int i = 0; i < p.n_tiles; ++i) {
+    const int last = p.n_tiles - 1;
+    for (int i = last; i >= 0; --i) {
+      if (i == p.n_tiles - 2) {        // the remaining S tiles (issued while the last tile's pass 1 ran)
+        mbar_wait(&bar_s[1], 0);
+        tc_fence_after();
+      }
       const bool ok = rl < p.nrows[i];
       const int row = p.row0[i] + rl;                       // keys 0..row are visible (tril mask, minGPT.py:65-68, :82)
-      // last key any row of this warp can see -> number of 32-column chunks this warp has to load (warp-uniform)
+      // last key any row of this warp can see -> number of 32-column chunks to load (warp-uniform)
       const int wlast_rl = (quarter * 32 + 31 < p.nrows[i]) ? quarter * 32 + 31 : p.nrows[i] - 1;
       const int wkeys = (wlast_rl >= quarter * 32) ? p.row0[i] + wlast_rl + 1 : 0;
       const int nch_load = (wkeys + 31) / 32;
       const int nch_all = (p.kpad[i] + 31) / 32;
+      // chunks entirely at or below the diagonal for EVERY row of this warp need no mask (all 32 rows valid)
+      const int nch_full = (quarter * 32 + 31 < p.nrows[i]) ? (p.row0[i] + quarter * 32 + 1) / 32 : 0;
       const uint32_t s_addr = lane_base + p.scol[i];
 
-      // pass 1: exact row maximum of the scaled scores
+      // pass 1: exact row maximum of the scores (this thread's chunks, two TMEM loads in flight), combined with the
+      // other half's through shared memory
       float m = -INFINITY;
-      for (int c = 0; c < nch_load; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(s_addr + c * 32, r);
-        tmem_ld_wait();
+      auto chunk_max = [&](const uint32_t (&r)[32], int c) {
+        if (c < nch_full) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j <= row) m = fmaxf(m, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 2) m = max3(m, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j <= row) m = fmaxf(m, __uint_as_float(r[j]));
+        }
+      };
+      for (int c = half; c < nch_load; c += 4) {
+        uint32_t r0[32], r1[32];
+        const bool two = c + 2 < nch_load;
+        tmem_ld_32x32(s_addr + c * 32, r0);
+        if (two) tmem_ld_32x32(s_addr + (c + 2) * 32, r1);
+        tmem_ld_wait();
+        chunk_max(r0, c);
+        if (two) chunk_max(r1, c + 2);
       }
-      m *= scale2;
-      // the previous tile's output: its P V MMAs ran while pass 1 was reading S_i; they must be complete before P_i
-      // overwrites the shared-memory region they read from
-      if (i > 0) epilogue(i - 1, l_prev);
+      s_m[half * 128 + rl] = m;
+      AT_STAMP();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      m = fmaxf(s_m[rl], s_m[128 + rl]) * scale2;
+      // P_i goes to the region tile i + 2 used (consecutive tiles alternate between two regions, so P V of tile i + 1 never
+      // has to be awaited here): that tile's MMAs finished long ago -- its epilogue runs now.  The last tile (processed
+      // first) writes over Q | K, so every S MMA must be done.
+      if (i == last) mbar_wait(&bar_s[1], 0);
+      else if (i + 2 <= last) epilogue(i + 2, lsum[i + 2]);
+      AT_STAMP();
 
       // pass 2: p = exp2(s' - m'), row sum, bf16 P into the A-operand layout (masked / unloaded columns are zeros)
       float l = 0.f;
-      for (int c = 0; c < nch_all; ++c) {
+      for (int c = half; c < nch_all; c += 2) {
         uint32_t pk[16];
         if (c < nch_load) {
           uint32_t r[32];
           tmem_ld_32x32(s_addr + c * 32, r);
           tmem_ld_wait();
           float e[32];
+          if (c < nch_full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, -m));
-            e[j] = (ok && c * 32 + j <= row) ? v : 0.f;
-            l += e[j];
+            for (int j = 0; j < 32; ++j) {
+              e[j] = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, -m));
+              l += e[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, -m));
+              e[j] = (ok && c * 32 + j <= row) ? v : 0.f;
+              l += e[j];
+            }
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
@@ -218,7 +314,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParam
           for (int j = 0; j < 16; ++j) pk[j] = 0u;
         }
         // row rl of P block (c >> 1): 128-byte row, 16-byte chunks (c & 1) * 4 + j, XOR-swizzled with the row phase
-        const uint32_t prow = smem_u32(sP) + (c >> 1) * AT_TILE_BYTES + (rl >> 3) * 1024 + (rl & 7) * 128;
+        const uint32_t prow = smem_u32(((last - i) & 1) ? sP1 : sP) + (c >> 1) * AT_TILE_BYTES + (rl >> 3) * 1024 + (rl & 7) * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int ch = ((c & 1) * 4 + j) ^ (rl & 7);
@@ -227,16 +323,22 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParam
                        : "memory");
         }
       }
+      s_l[half * 128 + rl] = l;
       fence_proxy_async_smem();     // generic-proxy writes of P -> visible to the tensor core
       tc_fence_before();            // our TMEM reads of S_i are done: O_i may overwrite its first 64 columns
       mbar_arrive(&bar_p[i]);
-      l_prev = l;
+      AT_STAMP();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      lsum[i] = s_l[rl] + s_l[128 + rl];
     }
-    epilogue(p.n_tiles - 1, l_prev);
+    if (last >= 1) epilogue(1, lsum[1]);
+    epilogue(0, lsum[0]);
+    AT_STAMP();
   }
 
   tc_fence_before();
   __syncthreads();
+  AT_STAMP();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
@@ -265,7 +367,21 @@ static bool attn_tc_plan(int T, AttnTcParams& p) {
   if (col > 512) return false;
   p.tmem_cols = 32;
   while (p.tmem_cols < col) p.tmem_cols *= 2;
-  p.nkb = (p.kpad[p.n_tiles - 1] + 127) / 128;
+  p.kmax = p.kpad[p.n_tiles - 1];
+  p.q0_small = (p.nrows[0] <= 16) ? 1 : 0;
+  // Q tiles last-first; a short tile 0 takes 2 KB (the MMA reads 128 rows from there: the tail is K data -- finite, and it
+  // only reaches accumulator rows nobody reads unmasked)
+  int off = 0;
+  for (int i = p.n_tiles - 1; i >= 0; --i) {
+    p.qoff[i] = off;
+    off += (i == 0 && p.q0_small) ? 16 * 128 : AT_TILE_BYTES;
+  }
+  p.koff = off;
+  const int qk = off + p.kmax * 128;
+  const int pt = ((p.kmax + 63) / 64) * AT_TILE_BYTES;
+  p.pk_bytes = ((qk > pt ? qk : pt) + 1023) & ~1023;
+  if (p.pk_bytes < p.qoff[0] + AT_TILE_BYTES) p.pk_bytes = p.qoff[0] + AT_TILE_BYTES;   // tile 0's 128-row read stays inside
+  p.p1_bytes = (p.n_tiles >= 2) ? ((p.kpad[p.n_tiles - 2] + 63) / 64) * AT_TILE_BYTES : 0;
   return true;
 }
 
@@ -275,26 +391,26 @@ bool gpt_attention_prefill_tc_supported(int T) {
   return !off && attn_tc_plan(T, p);
 }
 
-int gpt_attention_prefill_tc(const __nv_bfloat16* qkv, int B, int T, int nh, __nv_bfloat16* y, cudaStream_t s) {
+int gpt_attention_prefill_tc(const __nv_bfloat16* qkv, int B, int T, int nh, __nv_bfloat16* y, cudaStream_t s, long long* trace) {
   AttnTcParams p;
   MGV_REQUIRE(attn_tc_plan(T, p), "attention (tcgen05): T=%d unsupported", T);
   if (B == 0) return MGV_OK;
   p.nh = nh;
   p.C = nh * GPT_HEAD_DIM;
   p.y = y;
-  CUtensorMap tm;
+  p.trace = trace;
+  CUtensorMap tm, tm16;
   // qkv as (3C, T, B): a box never crosses into the next sequence, rows >= T are zero-filled
   MGV_TRY(make_tmap_nhwc_bf16(&tm, qkv, 3 * p.C, T, B, 1, GPT_HEAD_DIM, 128, 1, 1));
-  const int p_tiles = (p.kpad[p.n_tiles - 1] + 63) / 64;
-  const int pk_tiles = p.n_tiles + p.nkb > p_tiles ? p.n_tiles + p.nkb : p_tiles;
-  const size_t smem = static_cast<size_t>(pk_tiles + p.nkb) * AT_TILE_BYTES + 128 + 1024;
+  MGV_TRY(make_tmap_nhwc_bf16(&tm16, qkv, 3 * p.C, T, B, 1, GPT_HEAD_DIM, 16, 1, 1));
+  const size_t smem = static_cast<size_t>(p.pk_bytes) + static_cast<size_t>(p.kmax) * 128 + p.p1_bytes + 2048 + 128 + 1024;
   static unsigned long long attr_mask = 0;   // per device
   if (first_use_on_this_device(attr_mask)) {
     MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
   }
-  attn_prefill_tc_kernel<<<B * nh, AT_THREADS, smem, s>>>(tm, p);
+  attn_prefill_tc_kernel<<<B * nh, AT_THREADS, smem, s>>>(tm, tm16, p);
   MGV_CHECK_CUDA(cudaGetLastError());
   return MGV_OK;
 }

@@ -903,11 +903,16 @@ int gpt_layernorm(const float* x, const float* w, const float* b, int rows, int 
 
 int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_unmasked, __nv_bfloat16* y, float* att,
                           int att_T, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int Tmax, cudaStream_t s) {
+  // plain causal mask (n_unmasked <= 1 is the tril mask), no attention map, no cache fill: the tcgen05 kernel
+  if (att == nullptr && kcache == nullptr && n_unmasked <= 1 && T <= GPT_MAX_T && gpt_attention_prefill_tc_supported(T))
+    return gpt_attention_prefill_tc(qkv, B, T, nh, y, s);
+  return gpt_attention_prefill_mma(qkv, B, T, nh, n_unmasked, y, att, att_T, kcache, vcache, Tmax, s);
+}
+
+int gpt_attention_prefill_mma(const __nv_bfloat16* qkv, int B, int T, int nh, int n_unmasked, __nv_bfloat16* y, float* att,
+                              int att_T, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int Tmax, cudaStream_t s) {
   MGV_REQUIRE(T >= 1 && T <= GPT_MAX_T && (T + 15) / 16 <= 2 * FA_WARPS, "attention: T=%d exceeds %d", T, GPT_MAX_T);
   if (B == 0) return MGV_OK;
-  // plain causal mask (n_unmasked <= 1 is the tril mask), no attention map, no cache fill: the tcgen05 kernel
-  if (att == nullptr && kcache == nullptr && n_unmasked <= 1 && gpt_attention_prefill_tc_supported(T))
-    return gpt_attention_prefill_tc(qkv, B, T, nh, y, s);
   const int kpad = ceil_div(T, FA_BN) * FA_BN;
   const size_t smem = static_cast<size_t>(2 * kpad) * FA_LD * sizeof(__nv_bfloat16);
   static unsigned long long attr_mask = 0;   // per device (and per template instantiation)

@@ -25,10 +25,15 @@ int gpt_layernorm(const float* x, const float* w, const float* b, int rows, int 
 // kcache/vcache (optional): bf16 [B, nh, Tmax, 64] receive K and V of positions 0..T-1.
 int gpt_attention_prefill(const __nv_bfloat16* qkv, int B, int T, int nh, int n_unmasked, __nv_bfloat16* y, float* att,
                           int att_T, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int Tmax, cudaStream_t s);
+// the mma.sync kernel (every mask / output option)
+int gpt_attention_prefill_mma(const __nv_bfloat16* qkv, int B, int T, int nh, int n_unmasked, __nv_bfloat16* y, float* att,
+                              int att_T, __nv_bfloat16* kcache, __nv_bfloat16* vcache, int Tmax, cudaStream_t s);
 // The same contract on tcgen05 / TMEM / TMA (attn_prefill_tc.cu) for the plain causal mask without the attention-map
 // output and without the KV-cache fill; gpt_attention_prefill routes to it when `supported(T)`.
 bool gpt_attention_prefill_tc_supported(int T);
-int gpt_attention_prefill_tc(const __nv_bfloat16* qkv, int B, int T, int nh, __nv_bfloat16* y, cudaStream_t s);
+// trace (optional, diagnostics): 48 clock64 stamps of the middle CTA (tools/attn_trace.py)
+int gpt_attention_prefill_tc(const __nv_bfloat16* qkv, int B, int T, int nh, __nv_bfloat16* y, cudaStream_t s,
+                             long long* trace = nullptr);
 
 // One decode position: q,k,v fp32 [B, 3C] for position *pos_ptr; appends k,v to the cache and
 // attends over positions 0..pos.  att_rows (optional): fp32 [B, nh, Tatt, Tatt] pre-zeroed; entries 0..pos of row pos are written.

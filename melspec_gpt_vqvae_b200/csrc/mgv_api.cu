@@ -3,6 +3,7 @@
 #include <exception>
 #include "gemm_tc.cuh"
 #include "vqvae_kernels.cuh"
+#include "gpt_kernels.cuh"
 #include "gpt.cuh"
 #include "gpt_train.cuh"
 #include "melgan.cuh"
@@ -409,6 +410,21 @@ int mgv_test_conv3x3(int impl, const void* x, const void* w, const float* bias, 
   a.bn = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
   a.stream = static_cast<cudaStream_t>(stream);
   return impl == 0 ? gemm_bf16_tc(a) : gemm_bf16_ref(a);
+  MGV_API_END
+}
+
+int mgv_test_attention_prefill(int impl, const void* qkv, int B, int T, int nh, void* y, int64_t* trace, mgv_stream_t stream) {
+  MGV_API_BEGIN
+  MGV_TRY(check_device());
+  MGV_REQUIRE(qkv && y && B >= 0 && nh >= 1, "attention_prefill: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (impl == 0) {
+    MGV_REQUIRE(gpt_attention_prefill_tc_supported(T), "attention_prefill: T=%d is not covered by the tcgen05 kernel", T);
+    return gpt_attention_prefill_tc(static_cast<const __nv_bfloat16*>(qkv), B, T, nh, static_cast<__nv_bfloat16*>(y), s,
+                                    reinterpret_cast<long long*>(trace));
+  }
+  return gpt_attention_prefill_mma(static_cast<const __nv_bfloat16*>(qkv), B, T, nh, 0, static_cast<__nv_bfloat16*>(y), nullptr, 0,
+                                   nullptr, nullptr, 0, s);
   MGV_API_END
 }
 

@@ -263,3 +263,27 @@ def test_odd_head_count_config_vs_oracle():
     agree = float((xs.cpu() == o_xs).float().mean())
     print("3-head config greedy agreement with the oracle: %.3f" % agree)
     assert agree > 0.9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("B,T,nh", [(3, 265, 16), (2, 272, 4), (2, 257, 4), (2, 256, 4), (3, 200, 2), (2, 129, 4), (2, 128, 4),
+                                    (5, 40, 3), (2, 9, 2), (1, 1, 1)])
+def test_prefill_attention_kernels_vs_sdpa(impl, B, T, nh):
+    """CausalSelfAttention core (reference transformer/minGPT.py:78-86: tril mask, softmax(q k^T / sqrt(d)) v) of both
+    prefill kernels -- tcgen05 (impl 0: S in TMEM, P through shared memory) and mma.sync (impl 1) -- against fp32 SDPA
+    on the same bf16 q, k, v.  Tolerance: P and the output are rounded to bf16 (2^-8 relative), |v| <= ~4."""
+    from melspec_gpt_vqvae_b200 import _lib
+    L = _lib.load()
+    C = nh * 64
+    torch.manual_seed(B * 1000 + T)
+    qkv = torch.randn(B * T, 3 * C, device="cuda").bfloat16()
+    q, k, v = [t.float().view(B, T, nh, 64).transpose(1, 2) for t in qkv.split(C, dim=1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B * T, C)
+    y = torch.full((B * T, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(L.mgv_test_attention_prefill(impl, _lib.ptr(qkv), B, T, nh, _lib.ptr(y), None,
+                                            _lib.stream_ptr(torch.device("cuda", 0))))
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all()
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 0.03, "max |err| %.4f" % err
