@@ -66,7 +66,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm16, const AttnTcParams p) {
+attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm16,
+                       const __grid_constant__ CUtensorMap tm32, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // Q tiles, last tile first (a short tile 0 takes 2 KB) } reused for P
@@ -99,6 +100,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tm);
     prefetch_tensormap(&tm16);
+    prefetch_tensormap(&tm32);
     mbar_init(bar_qk, 1);
     mbar_init(bar_q, 1);
     mbar_init(bar_v, 1);
@@ -118,8 +120,14 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
     const int last = p.n_tiles - 1;
     const uint32_t q0_bytes = p.q0_small ? 16 * 128 : AT_TILE_BYTES;
     mbar_arrive_expect_tx(bar_qk, (last == 0 ? q0_bytes : AT_TILE_BYTES) + static_cast<uint32_t>(p.kmax) * 128);
-    tma_load_4d(sQ + p.qoff[last], (last == 0 && p.q0_small) ? &tm16 : &tm, bar_qk, h * GPT_HEAD_DIM, p.row0[last], b, 0,
-                kEvictFirst);
+    if (last > 0) {
+      // the last tile's 32-row quarters go to shared memory in REVERSE order (see the softmax warps: load balance)
+      for (int q = 0; q < 4; ++q)
+        tma_load_4d(sQ + p.qoff[last] + q * 32 * 128, &tm32, bar_qk, h * GPT_HEAD_DIM, p.row0[last] + (3 - q) * 32, b, 0,
+                    kEvictFirst);
+    } else {
+      tma_load_4d(sQ + p.qoff[last], p.q0_small ? &tm16 : &tm, bar_qk, h * GPT_HEAD_DIM, p.row0[last], b, 0, kEvictFirst);
+    }
     for (int j = 0; j < kfull; ++j)
       tma_load_4d(sK + j * AT_TILE_BYTES, &tm, bar_qk, p.C + h * GPT_HEAD_DIM, j * 128, b, 0, kEvictFirst);
     for (int j = 0; j < krem; ++j)
@@ -203,6 +211,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int rl = quarter * 32 + lane;
+    const int last = p.n_tiles - 1;
+    // Tile row (TMEM lane) -> sequence row.  A warp's work grows with the number of keys its rows can see, and the lane
+    // quarter of a warp (= its SM sub-partition, with its one MUFU unit) is fixed.  With every tile in natural order
+    // quarter 3 would get the longest rows of every tile (T = 265: 15 chunks of 32 columns against 9 for quarter 0);
+    // the last tile is therefore stored with its quarters reversed: 12 / 11 / 11 / 11.
+    auto tile_row = [&](int i) { return (i == last && last > 0) ? (3 - quarter) * 32 + lane : rl; };
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     // 1/sqrt(d) (minGPT.py:81) folded with log2(e): probabilities are exp2(s' - max')
     const float scale2 = 1.4426950408889634f * 0.125f;
@@ -215,9 +229,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
     auto epilogue = [&](int i, float l) {
       mbar_wait(&bar_o[i], 0);
       tc_fence_after();
-      const bool ok = rl < p.nrows[i];
+      const int tr_ = tile_row(i);
+      const bool ok = tr_ < p.nrows[i];
       const float inv = ok ? 1.0f / l : 0.f;
-      __nv_bfloat16* dst = p.y + (static_cast<long long>(b) * p.T + p.row0[i] + rl) * p.C + h * GPT_HEAD_DIM + half * 32;
+      __nv_bfloat16* dst = p.y + (static_cast<long long>(b) * p.T + p.row0[i] + tr_) * p.C + h * GPT_HEAD_DIM + half * 32;
       uint32_t r[32];
       tmem_ld_32x32(lane_base + p.ocol[i] + half * 32, r);
       tmem_ld_wait();
@@ -234,21 +249,22 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
       }
     };
 
-    const int last = p.n_tiles - 1;
     for (int i = last; i >= 0; --i) {
       if (i == p.n_tiles - 2) {        // the remaining S tiles (issued while the last tile's pass 1 ran)
         mbar_wait(&bar_s[1], 0);
         tc_fence_after();
       }
-      const bool ok = rl < p.nrows[i];
-      const int row = p.row0[i] + rl;                       // keys 0..row are visible (tril mask, minGPT.py:65-68, :82)
+      const int trow = tile_row(i);
+      const int q0row = trow - lane;                        // first tile row of this warp
+      const bool ok = trow < p.nrows[i];
+      const int row = p.row0[i] + trow;                     // keys 0..row are visible (tril mask, minGPT.py:65-68, :82)
       // last key any row of this warp can see -> number of 32-column chunks to load (warp-uniform)
-      const int wlast_rl = (quarter * 32 + 31 < p.nrows[i]) ? quarter * 32 + 31 : p.nrows[i] - 1;
-      const int wkeys = (wlast_rl >= quarter * 32) ? p.row0[i] + wlast_rl + 1 : 0;
+      const int wlast_rl = (q0row + 31 < p.nrows[i]) ? q0row + 31 : p.nrows[i] - 1;
+      const int wkeys = (wlast_rl >= q0row) ? p.row0[i] + wlast_rl + 1 : 0;
       const int nch_load = (wkeys + 31) / 32;
       const int nch_all = (p.kpad[i] + 31) / 32;
       // chunks entirely at or below the diagonal for EVERY row of this warp need no mask (all 32 rows valid)
-      const int nch_full = (quarter * 32 + 31 < p.nrows[i]) ? (p.row0[i] + quarter * 32 + 1) / 32 : 0;
+      const int nch_full = (q0row + 31 < p.nrows[i]) ? (p.row0[i] + q0row + 1) / 32 : 0;
       const uint32_t s_addr = lane_base + p.scol[i];
 
       // pass 1: exact row maximum of the scores (this thread's chunks, two TMEM loads in flight), combined with the
@@ -399,10 +415,11 @@ int gpt_attention_prefill_tc(const __nv_bfloat16* qkv, int B, int T, int nh, __n
   p.C = nh * GPT_HEAD_DIM;
   p.y = y;
   p.trace = trace;
-  CUtensorMap tm, tm16;
+  CUtensorMap tm, tm16, tm32;
   // qkv as (3C, T, B): a box never crosses into the next sequence, rows >= T are zero-filled
   MGV_TRY(make_tmap_nhwc_bf16(&tm, qkv, 3 * p.C, T, B, 1, GPT_HEAD_DIM, 128, 1, 1));
   MGV_TRY(make_tmap_nhwc_bf16(&tm16, qkv, 3 * p.C, T, B, 1, GPT_HEAD_DIM, 16, 1, 1));
+  MGV_TRY(make_tmap_nhwc_bf16(&tm32, qkv, 3 * p.C, T, B, 1, GPT_HEAD_DIM, 32, 1, 1));
   const size_t smem = static_cast<size_t>(p.pk_bytes) + static_cast<size_t>(p.kmax) * 128 + p.p1_bytes + 2048 + 128 + 1024;
   static unsigned long long attr_mask = 0;   // per device
   if (first_use_on_this_device(attr_mask)) {
@@ -410,7 +427,7 @@ int gpt_attention_prefill_tc(const __nv_bfloat16* qkv, int B, int T, int nh, __n
     MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
   }
-  attn_prefill_tc_kernel<<<B * nh, AT_THREADS, smem, s>>>(tm, tm16, p);
+  attn_prefill_tc_kernel<<<B * nh, AT_THREADS, smem, s>>>(tm, tm16, tm32, p);
   MGV_CHECK_CUDA(cudaGetLastError());
   return MGV_OK;
 }
