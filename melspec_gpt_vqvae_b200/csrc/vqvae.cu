@@ -111,6 +111,14 @@ struct Vqvae {
   int gn_slots = 0;
   int* flag = nullptr;
   long long launches = 0;
+  // CUDA graph of the decoder (vqvae_decode) and the staging buffers its captured pointers refer to
+  cudaGraph_t dec_graph = nullptr;
+  cudaGraphExec_t dec_exec = nullptr;
+  int dec_graph_B = 0, eager_B = 0;
+  long long dec_graph_launches = 0;
+  cudaStream_t cap_stream = nullptr;
+  long long* idx_stage = nullptr;   // [ws_B, 265]
+  float* mel_stage = nullptr;       // [ws_B, 80, 848]
 };
 
 namespace {
@@ -228,6 +236,15 @@ int ensure_ws(Vqvae* v, int B) {
   cudaFree(v->f32buf); v->f32buf = nullptr;
   cudaFree(v->gn_slab); v->gn_slab = nullptr;
   cudaFree(v->gn_part); v->gn_part = nullptr;
+  cudaFree(v->idx_stage); v->idx_stage = nullptr;
+  cudaFree(v->mel_stage); v->mel_stage = nullptr;
+  if (v->dec_exec) {   // the captured launches point into the buffers that were just freed
+    cudaGraphExecDestroy(v->dec_exec);
+    cudaGraphDestroy(v->dec_graph);
+    v->dec_exec = nullptr;
+    v->dec_graph = nullptr;
+  }
+  v->eager_B = 0;
   v->ws_B = 0;
   const size_t act = static_cast<size_t>(B) * MEL_H * MEL_W * CH;  // largest activation (elements)
   for (auto& p : v->buf) MGV_CHECK_CUDA(cudaMalloc(&p, act * 2));
@@ -235,6 +252,8 @@ int ensure_ws(Vqvae* v, int B) {
   v->gn_slots = 96;
   MGV_CHECK_CUDA(cudaMalloc(&v->gn_slab, static_cast<size_t>(v->gn_slots) * B * 64 * 4));
   MGV_CHECK_CUDA(cudaMalloc(&v->gn_part, static_cast<size_t>(B) * MAX_TILES_PER_IMAGE * 64 * 4));
+  MGV_CHECK_CUDA(cudaMalloc(&v->idx_stage, static_cast<size_t>(B) * LAT_H * LAT_W * 8));
+  MGV_CHECK_CUDA(cudaMalloc(&v->mel_stage, static_cast<size_t>(B) * MEL_H * MEL_W * 4));
   v->ws_B = B;
   return MGV_OK;
 }
@@ -438,6 +457,11 @@ int vqvae_destroy(Vqvae* v) {
   cudaFree(v->gn_slab);
   cudaFree(v->gn_part);
   cudaFree(v->flag);
+  cudaFree(v->idx_stage);
+  cudaFree(v->mel_stage);
+  if (v->dec_exec) cudaGraphExecDestroy(v->dec_exec);
+  if (v->dec_graph) cudaGraphDestroy(v->dec_graph);
+  if (v->cap_stream) cudaStreamDestroy(v->cap_stream);
   delete v;
   return MGV_OK;
 }
@@ -491,24 +515,14 @@ int vqvae_load_weight(Vqvae* v, const char* name, const float* src, long long nu
   return MGV_OK;
 }
 
-// decode_to_img after code_reader (minGPT.py:515-528) / LitVQVAE.decode (:610-614)
-int vqvae_decode(Vqvae* v, const long long* idx, const float* quant_bchw, int B, float* mel_out, cudaStream_t s) {
-  MGV_REQUIRE(v && mel_out && ((idx != nullptr) != (quant_bchw != nullptr)), "vqvae_decode: need exactly one of idx / quant");
-  MGV_REQUIRE(B >= 0, "vqvae_decode: B=%d", B);
-  MGV_TRY(check_loaded(v, "_decoder.", "post_quant_conv.", idx ? "_vq_vae." : nullptr));
-  if (B == 0) return MGV_OK;
-  v->launches = 0;
-  MGV_TRY(ensure_ws(v, B));
+// every launch of the decoder for B images, enqueued on s (the gather table is valid; no host synchronisation inside, so
+// the sequence can be captured into a CUDA graph)
+static int decode_body(Vqvae* v, const long long* idx, const float* quant_bchw, int B, float* mel_out, cudaStream_t s) {
   Ctx c{v, B, s};
   __nv_bfloat16 *h = v->buf[0], *o = v->buf[1], *ta = v->buf[2], *tb = v->buf[3], *ts = v->buf[4];
   const long long lat_rows = static_cast<long long>(B) * LAT_H * LAT_W;
   // ---- z_q -> post_quant_conv (fused into a table lookup when decoding codes)
   if (idx) {
-    if (!v->table_valid) {
-      MGV_TRY(vqvae_build_gather_table(v->codebook, v->pq_w, v->pq_b, v->K, v->D, Z_CH, v->table, s));
-      v->table_valid = true;
-      v->launches++;
-    }
     MGV_TRY(vqvae_gather_rows(idx, v->table, lat_rows, Z_CH, v->K, ta, v->flag, s));
     v->launches++;
   } else {
@@ -563,6 +577,68 @@ int vqvae_decode(Vqvae* v, const long long* idx, const float* quant_bchw, int B,
   MGV_TRY(vqvae_norm_swish_conv_out(h, st, v->dec_norm_out.w, v->dec_norm_out.b, v->dec_conv_out_w, v->dec_conv_out_b, B,
                                     H, W, CH, mel_out, s));
   v->launches += 1;
+  return MGV_OK;
+}
+
+// decode_to_img after code_reader (minGPT.py:515-528) / LitVQVAE.decode (:610-614)
+//
+// The decoder is ~150 launches, the first ~60 of which (5x53 and 10x106 levels) last 5-30 us each: launched one by one
+// (two tensor-map encodes + a launch per GEMM) the host falls behind and the GPU idles ~1.6 ms of a 22 ms decode at
+// B = 64.  The code path therefore replays a CUDA graph of the whole decoder: the first call at a batch size runs
+// eagerly (function attributes, lazily built state), the second captures, later ones replay.  Indices and mels go
+// through handle-owned staging buffers so that the captured pointers never change.
+int vqvae_decode(Vqvae* v, const long long* idx, const float* quant_bchw, int B, float* mel_out, cudaStream_t s) {
+  MGV_REQUIRE(v && mel_out && ((idx != nullptr) != (quant_bchw != nullptr)), "vqvae_decode: need exactly one of idx / quant");
+  MGV_REQUIRE(B >= 0, "vqvae_decode: B=%d", B);
+  MGV_TRY(check_loaded(v, "_decoder.", "post_quant_conv.", idx ? "_vq_vae." : nullptr));
+  if (B == 0) return MGV_OK;
+  v->launches = 0;
+  MGV_TRY(ensure_ws(v, B));
+  if (idx && !v->table_valid) {
+    MGV_TRY(vqvae_build_gather_table(v->codebook, v->pq_w, v->pq_b, v->K, v->D, Z_CH, v->table, s));
+    v->table_valid = true;
+    v->launches++;
+  }
+  static const bool no_graph = getenv("MGV_VQVAE_NO_GRAPH") != nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  MGV_CHECK_CUDA(cudaStreamIsCapturing(s, &cap));
+  const bool graph_ok = idx && !no_graph && cap == cudaStreamCaptureStatusNone;
+  if (graph_ok && v->dec_exec == nullptr && v->eager_B == B) {
+    // second call at this batch size: capture (on the handle's own stream -- the caller's may be the legacy stream)
+    if (!v->cap_stream) MGV_CHECK_CUDA(cudaStreamCreateWithFlags(&v->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    MGV_CHECK_CUDA(cudaStreamBeginCapture(v->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const long long before = v->launches;
+    const int rc = decode_body(v, v->idx_stage, nullptr, B, v->mel_stage, v->cap_stream);
+    v->dec_graph_launches = v->launches - before;
+    v->launches = before;
+    const cudaError_t ce = cudaStreamEndCapture(v->cap_stream, &graph);
+    if (rc != MGV_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    MGV_CHECK_CUDA(ce);
+    MGV_CHECK_CUDA(cudaGraphInstantiate(&v->dec_exec, graph, 0));
+    v->dec_graph = graph;
+    v->dec_graph_B = B;
+  }
+  if (graph_ok && v->dec_exec != nullptr && v->dec_graph_B == B) {
+    MGV_CHECK_CUDA(cudaMemcpyAsync(v->idx_stage, idx, static_cast<size_t>(B) * LAT_H * LAT_W * 8, cudaMemcpyDeviceToDevice, s));
+    MGV_CHECK_CUDA(cudaGraphLaunch(v->dec_exec, s));
+    MGV_CHECK_CUDA(cudaMemcpyAsync(mel_out, v->mel_stage, static_cast<size_t>(B) * MEL_H * MEL_W * 4, cudaMemcpyDeviceToDevice, s));
+    v->launches += v->dec_graph_launches;
+  } else {
+    MGV_TRY(decode_body(v, idx, quant_bchw, B, mel_out, s));
+    if (graph_ok) {
+      if (v->dec_exec) {   // another batch size: drop the old graph, this size captures on its next call
+        cudaGraphExecDestroy(v->dec_exec);
+        cudaGraphDestroy(v->dec_graph);
+        v->dec_exec = nullptr;
+        v->dec_graph = nullptr;
+      }
+      v->eager_B = B;
+    }
+  }
   if (idx) {
     int flag = 0;
     MGV_CHECK_CUDA(cudaMemcpyAsync(&flag, v->flag, sizeof(int), cudaMemcpyDeviceToHost, s));
