@@ -47,6 +47,8 @@ struct AttnTcParams {
   int tmem_cols;      // power of two
   __nv_bfloat16* y;   // [B*T, C]
   long long* trace;   // optional (diagnostics): clock64 stamps of CTA 0, [16] per recording thread
+  int heads;          // persistent form: B * nh
+  int buf_bytes;      // persistent form: bytes of one head's Q | K | V buffer
 };
 
 // kind::f16, A = bf16 K-major, B = bf16 K-major (b_mn = 0) or MN-major (b_mn = 1), D = f32
@@ -361,6 +363,297 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent form for the three-tile shapes (257 <= T <= 272: the VAS / VGGSound block size 265).  The one-head-per-CTA
+// kernel above spends ~40 % of a CTA's life in fixed costs (launch and turnover, barrier set-up, TMEM allocation, waiting
+// for its first loads, the last epilogues), and TMEM (496 of 512 columns) keeps a second CTA off the SM.  Here one CTA per
+// SM walks over its heads with TWO Q | K | V buffers: the next head's operands land while the current head is computed,
+// and the next head's S MMAs are issued as soon as the TMEM columns they overwrite have been consumed (S_2 of the next
+// head after the epilogue of tile 2, S_1 / S_0 at the head boundary), so the softmax warps never wait for a load or for S.
+// Shared memory (T = 265): 2 x (Q 34 KB | K 34 KB | V 34 KB) + one 16 KB block for the fifth P block of the long tile
+// (P blocks 0..3 reuse the current buffer's Q | K, dead once its S MMAs are done) = 220 KB.
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_prefill_tc_persist_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm16,
+                               const __grid_constant__ CUtensorMap tm32, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ptail = smem + 2 * p.buf_bytes;                      // P block 4 (keys 256..) of the long tile
+  float* s_m = reinterpret_cast<float*>(ptail + AT_TILE_BYTES);  // [2][128]
+  float* s_l = s_m + 256;                                        // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_l + 256);
+  uint64_t* bar_qk = bars;         // [2] per buffer: Q_2 + K landed
+  uint64_t* bar_q = bars + 2;      // [2] per buffer: Q_1 + Q_0 landed
+  uint64_t* bar_v = bars + 4;      // [2] per buffer: V landed
+  uint64_t* bar_s2 = bars + 6;     // per head: S_2 complete
+  uint64_t* bar_sall = bars + 7;   // per head: S_1, S_0 complete
+  uint64_t* bar_p = bars + 8;      // [3] per head: P_i written (256 arrivals)
+  uint64_t* bar_o = bars + 11;     // [3] per head: O_i complete
+  uint64_t* bar_oc = bars + 14;    // [3] per head: O_i read by every softmax thread (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grid = gridDim.x;
+  const int n_my = (p.heads - static_cast<int>(blockIdx.x) + grid - 1) / grid;
+  const int v_off = p.pk_bytes;                                  // V inside a head's buffer
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tm);
+    prefetch_tensormap(&tm16);
+    prefetch_tensormap(&tm32);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_qk[i], 1);
+      mbar_init(&bar_q[i], 1);
+      mbar_init(&bar_v[i], 1);
+    }
+    mbar_init(bar_s2, 1);
+    mbar_init(bar_sall, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bar_p[i], AT_THREADS - 64);
+      mbar_init(&bar_o[i], 1);
+      mbar_init(&bar_oc[i], AT_THREADS - 64);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int kfull = p.kmax / 128, krem = (p.kmax - kfull * 128) / 16;
+      const uint32_t q0_bytes = p.q0_small ? 16 * 128 : AT_TILE_BYTES;
+      auto issue_loads = [&](int it) {
+        const int head = blockIdx.x + it * grid;
+        const int b = head / p.nh, h = head - b * p.nh;
+        uint8_t* buf = smem + (it & 1) * p.buf_bytes;
+        const int bi = it & 1;
+        mbar_arrive_expect_tx(&bar_qk[bi], AT_TILE_BYTES + static_cast<uint32_t>(p.kmax) * 128);
+        for (int q = 0; q < 4; ++q)     // quarters of the long tile in reverse order (load balance of the softmax warps)
+          tma_load_4d(buf + p.qoff[2] + q * 32 * 128, &tm32, &bar_qk[bi], h * GPT_HEAD_DIM, p.row0[2] + (3 - q) * 32, b, 0, kEvictFirst);
+        for (int j = 0; j < kfull; ++j)
+          tma_load_4d(buf + p.koff + j * AT_TILE_BYTES, &tm, &bar_qk[bi], p.C + h * GPT_HEAD_DIM, j * 128, b, 0, kEvictFirst);
+        for (int j = 0; j < krem; ++j)
+          tma_load_4d(buf + p.koff + (kfull * 128 + j * 16) * 128, &tm16, &bar_qk[bi], p.C + h * GPT_HEAD_DIM, kfull * 128 + j * 16, b, 0,
+                      kEvictFirst);
+        mbar_arrive_expect_tx(&bar_q[bi], AT_TILE_BYTES + q0_bytes);
+        tma_load_4d(buf + p.qoff[1], &tm, &bar_q[bi], h * GPT_HEAD_DIM, p.row0[1], b, 0, kEvictFirst);
+        tma_load_4d(buf + p.qoff[0], p.q0_small ? &tm16 : &tm, &bar_q[bi], h * GPT_HEAD_DIM, p.row0[0], b, 0, kEvictFirst);
+        mbar_arrive_expect_tx(&bar_v[bi], static_cast<uint32_t>(p.kmax) * 128);
+        for (int j = 0; j < kfull; ++j)
+          tma_load_4d(buf + v_off + j * AT_TILE_BYTES, &tm, &bar_v[bi], 2 * p.C + h * GPT_HEAD_DIM, j * 128, b, 0, kEvictFirst);
+        for (int j = 0; j < krem; ++j)
+          tma_load_4d(buf + v_off + (kfull * 128 + j * 16) * 128, &tm16, &bar_v[bi], 2 * p.C + h * GPT_HEAD_DIM, kfull * 128 + j * 16, b,
+                      0, kEvictFirst);
+      };
+      auto issue_s = [&](int it, int i) {
+        uint8_t* buf = smem + (it & 1) * p.buf_bytes;
+        const uint64_t da = make_smem_desc_sw128(smem_u32(buf + p.qoff[i]));
+        for (int n0 = 0; n0 < p.kpad[i]; n0 += 256) {
+          const int n = (p.kpad[i] - n0 < 256) ? p.kpad[i] - n0 : 256;
+          const uint64_t db = make_smem_desc_sw128(smem_u32(buf + p.koff) + n0 * 128);
+          const uint32_t idesc = at_idesc(128, n, 0);
+#pragma unroll
+          for (int k = 0; k < GPT_HEAD_DIM / 16; ++k)
+            umma_bf16(tmem_base + p.scol[i] + n0, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+        }
+      };
+      const uint32_t idesc_pv = at_idesc(128, GPT_HEAD_DIM, 1);
+      auto issue_pv = [&](int it, int i) {
+        uint8_t* buf = smem + (it & 1) * p.buf_bytes;
+        const int ksteps = p.kpad[i] / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t pa = (ks < 16) ? smem_u32(buf) + (ks >> 2) * AT_TILE_BYTES : smem_u32(ptail);
+          const uint64_t da = make_smem_desc_sw128(pa + (ks & 3) * 32);
+          const uint64_t db = make_smem_desc_mn_sw128(smem_u32(buf + v_off) + ks * 2048, 8192, 1024);
+          umma_bf16(tmem_base + p.ocol[i], da, db, idesc_pv, ks != 0 ? 1u : 0u);
+        }
+      };
+
+      issue_loads(0);
+      if (n_my > 1) issue_loads(1);
+      mbar_wait(&bar_qk[0], 0);
+      tc_fence_after();
+      issue_s(0, 2);
+      tc_commit(bar_s2);
+      for (int it = 0; it < n_my; ++it) {
+        const int bi = it & 1;
+        const uint32_t ph = it & 1, lph = (it >> 1) & 1, pph = (it - 1) & 1;
+        // S_1, S_0 of this head: their columns held S_1 / O_1 and S_0 of the previous head
+        if (it > 0) mbar_wait(&bar_oc[1], pph);
+        mbar_wait(&bar_q[bi], lph);
+        tc_fence_after();
+        issue_s(it, 1);
+        issue_s(it, 0);
+        tc_commit(bar_sall);
+        // operands of the next head into the other buffer, once the previous head's last MMA has read it
+        if (it >= 1 && it + 1 < n_my) {
+          mbar_wait(&bar_o[0], pph);
+          issue_loads(it + 1);
+        }
+        mbar_wait(&bar_v[bi], lph);
+        mbar_wait(&bar_p[2], ph);
+        tc_fence_after();
+        issue_pv(it, 2);
+        tc_commit(&bar_o[2]);
+        mbar_wait(&bar_p[1], ph);
+        tc_fence_after();
+        issue_pv(it, 1);
+        tc_commit(&bar_o[1]);
+        if (it + 1 < n_my) {   // S_2 of the next head: O_2 of this one has been read, the next operands have landed
+          mbar_wait(&bar_oc[2], ph);
+          mbar_wait(&bar_qk[bi ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(it + 1, 2);
+          tc_commit(bar_s2);
+        }
+        mbar_wait(&bar_p[0], ph);
+        tc_fence_after();
+        issue_pv(it, 0);
+        tc_commit(&bar_o[0]);
+      }
+    }
+  } else if (warp >= 2) {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int rl = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float scale2 = 1.4426950408889634f * 0.125f;
+    auto tile_row = [&](int i) { return (i == 2) ? (3 - quarter) * 32 + lane : rl; };
+
+    for (int it = 0; it < n_my; ++it) {
+      const int head = blockIdx.x + it * grid;
+      const int b = head / p.nh, h = head - b * p.nh;
+      const uint32_t ph = it & 1;
+      uint8_t* buf = smem + (it & 1) * p.buf_bytes;
+      float lsum[3] = {0.f, 0.f, 0.f};
+
+      auto epilogue = [&](int i, float l) {
+        mbar_wait(&bar_o[i], ph);
+        tc_fence_after();
+        const int tr_ = tile_row(i);
+        const bool ok = tr_ < p.nrows[i];
+        const float inv = ok ? 1.0f / l : 0.f;
+        __nv_bfloat16* dst = p.y + (static_cast<long long>(b) * p.T + p.row0[i] + tr_) * p.C + h * GPT_HEAD_DIM + half * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(lane_base + p.ocol[i] + half * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_oc[i]);            // these TMEM columns may take the next head's S
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+            q.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+            q.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+            q.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + j * 8) = q;
+          }
+        }
+      };
+
+      mbar_wait(bar_s2, ph);
+      tc_fence_after();
+      for (int i = 2; i >= 0; --i) {
+        const int trow = tile_row(i);
+        const int q0row = trow - lane;
+        const bool ok = trow < p.nrows[i];
+        const int row = p.row0[i] + trow;
+        const int wlast_rl = (q0row + 31 < p.nrows[i]) ? q0row + 31 : p.nrows[i] - 1;
+        const int wkeys = (wlast_rl >= q0row) ? p.row0[i] + wlast_rl + 1 : 0;
+        const int nch_load = (wkeys + 31) / 32;
+        const int nch_all = (p.kpad[i] + 31) / 32;
+        const int nch_full = (q0row + 31 < p.nrows[i]) ? (p.row0[i] + q0row + 1) / 32 : 0;
+        const uint32_t s_addr = lane_base + p.scol[i];
+        if (i == 1) {                      // S_1, S_0 were issued at the head boundary
+          mbar_wait(bar_sall, ph);
+          tc_fence_after();
+        }
+        // pass 1: row maximum
+        float m = -INFINITY;
+        for (int c = half; c < nch_load; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32(s_addr + c * 32, r);
+          tmem_ld_wait();
+          if (c < nch_full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) m = max3(m, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j <= row) m = fmaxf(m, __uint_as_float(r[j]));
+          }
+        }
+        s_m[half * 128 + rl] = m;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        m = fmaxf(s_m[rl], s_m[128 + rl]) * scale2;
+        // P_i reuses the region P_{i+1} was read from: that tile's P V must be complete -- its epilogue runs here.
+        // The long tile writes over Q | K of this head: S_1 and S_0 must be complete.
+        if (i == 2) mbar_wait(bar_sall, ph);
+        else epilogue(i + 1, lsum[i + 1]);
+        // pass 2
+        float l = 0.f;
+        for (int c = half; c < nch_all; c += 2) {
+          uint32_t pk[16];
+          if (c < nch_load) {
+            uint32_t r[32];
+            tmem_ld_32x32(s_addr + c * 32, r);
+            tmem_ld_wait();
+            float e[32];
+            if (c < nch_full) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                e[j] = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, -m));
+                l += e[j];
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, -m));
+                e[j] = (ok && c * 32 + j <= row) ? v : 0.f;
+                l += e[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          }
+          const uint32_t pblk = (c < 8) ? smem_u32(buf) + (c >> 1) * AT_TILE_BYTES : smem_u32(ptail);
+          const uint32_t prow = pblk + (rl >> 3) * 1024 + (rl & 7) * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = ((c & 1) * 4 + j) ^ (rl & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (ch << 4)), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                         "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                         : "memory");
+          }
+        }
+        s_l[half * 128 + rl] = l;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bar_p[i]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        lsum[i] = s_l[rl] + s_l[128 + rl];
+      }
+      epilogue(0, lsum[0]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
 }  // namespace
 
 // true when attn_prefill_tc handles this shape (T rows in <= 3 query tiles whose score columns fit TMEM)
@@ -426,6 +719,27 @@ int gpt_attention_prefill_tc(const __nv_bfloat16* qkv, int B, int T, int nh, __n
     MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
+  }
+  // three-tile shapes (T = 265): one persistent CTA per SM with double-buffered operands
+  static const bool no_persist = getenv("MGV_ATTN_NO_PERSIST") != nullptr;
+  AttnTcParams pp = p;
+  pp.heads = B * nh;
+  pp.pk_bytes = (p.koff + p.kmax * 128 + 1023) & ~1023;   // Q | K only: the fifth P block has its own 16 KB here
+  pp.buf_bytes = pp.pk_bytes + p.kmax * 128;              // Q | K | V of one head
+  const size_t smem_p = 2 * static_cast<size_t>(pp.buf_bytes) + AT_TILE_BYTES + 2048 + 256 + 1024;
+  const bool persist = !no_persist && trace == nullptr && p.n_tiles == 3 && p.kmax > 256 && p.kmax <= 320 &&
+                       4 * AT_TILE_BYTES <= pp.pk_bytes && p.qoff[0] + AT_TILE_BYTES <= pp.pk_bytes && smem_p <= 227 * 1024;
+  if (persist) {
+    static unsigned long long attr_mask_p = 0;   // per device
+    if (first_use_on_this_device(attr_mask_p)) {
+      MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      MGV_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_persist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+    }
+    const int grid = pp.heads < num_sms() ? pp.heads : num_sms();
+    attn_prefill_tc_persist_kernel<<<grid, AT_THREADS, smem_p, s>>>(tm, tm16, tm32, pp);
+    MGV_CHECK_CUDA(cudaGetLastError());
+    return MGV_OK;
   }
   attn_prefill_tc_kernel<<<B * nh, AT_THREADS, smem, s>>>(tm, tm16, tm32, p);
   MGV_CHECK_CUDA(cudaGetLastError());

@@ -39,6 +39,33 @@ def test_decode_codes_vs_golden(model_and_sd):
     assert r2 <= 2 * yrms and e2 <= 2 * ymax
 
 
+def test_decode_graph_replay_tracks_batch_size_and_weights():
+    """The code path of the decoder replays a CUDA graph from its third call at a batch size on (first call eager, second
+    captures).  The replayed result must equal the eager one, survive a change of batch size in between (new capture) and
+    follow in-place weight updates (the graph holds pointers to the packed weights, which are rewritten in place)."""
+    sd = synthetic.synthetic_vqvae_state_dict(128, 256, seed=11, perturb=True)
+    m = make_vqvae(sd)
+    gen = torch.Generator().manual_seed(9)
+    codes = torch.randint(0, 128, (4, 265), generator=gen).cuda()
+    eager = m.decode_codes(codes).cpu()                      # call 1 at B=4: eager
+    captured = m.decode_codes(codes).cpu()                   # call 2: capture + launch
+    replayed = m.decode_codes(codes).cpu()                   # call 3: replay
+    assert torch.equal(eager, captured) and torch.equal(eager, replayed)
+    other = torch.randint(0, 128, (4, 265), generator=gen).cuda()
+    assert not torch.equal(m.decode_codes(other).cpu(), eager), "replay must read the new indices"
+    two = m.decode_codes(codes[:2]).cpu()                    # another batch size drops the graph
+    assert torch.equal(two, eager[:2])
+    for _ in range(3):                                       # eager, capture, replay at B=4 again
+        assert torch.equal(m.decode_codes(codes).cpu(), eager)
+    with torch.no_grad():
+        m._decoder.conv_out.bias.add_(0.5)                   # the tail adds this bias to every mel bin
+    shifted = m.decode_codes(codes).cpu()
+    assert torch.allclose(shifted, eager + 0.5, atol=1e-5), "weight update not visible through the replayed graph"
+    with pytest.raises(RuntimeError):                        # the index check still fires on the replay path
+        m.decode_codes(torch.full((4, 265), 128, dtype=torch.long, device="cuda"))
+    assert torch.equal(m.decode_codes(codes).cpu(), shifted)
+
+
 def test_decode_batch_independence_and_oracle(model_and_sd):
     m, sd = model_and_sd
     gen = torch.Generator().manual_seed(5)

@@ -21,6 +21,10 @@ for impl in (0, 1):
     _lib.check(L.mgv_test_attention_prefill(impl, _lib.ptr(qkv), B, T, nh, _lib.ptr(y), _lib.ptr(trace) if impl == 0 else None, S0))
     torch.cuda.synchronize()
     err = (y.float() - ref).abs().max().item()
+    y.zero_()
+    L.mgv_test_attention_prefill(impl, _lib.ptr(qkv), B, T, nh, _lib.ptr(y), None, S0)   # untraced: the persistent form where it applies
+    torch.cuda.synchronize()
+    err = max(err, (y.float() - ref).abs().max().item())
     for _ in range(3):
         L.mgv_test_attention_prefill(impl, _lib.ptr(qkv), B, T, nh, _lib.ptr(y), None, S0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
