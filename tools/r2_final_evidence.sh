@@ -18,10 +18,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-fi
     python tools/profile_targets.py decode 14 > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2f_vqvae_decode_launches_b64.csv \
     python tools/profile_targets.py vqvae 64 > /dev/null 2>&1
-# --set full: the last two 80x848 128->128 convolutions of a B=16 decode (conv2 of the last ResnetBlock carries the
+# --set full: the last two 80x848 128->128 convolutions of a B=64 decode (conv2 of the last ResnetBlock carries the
 # residual), and one launch of the tcgen05 prefill attention at bs=64
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_persist --launch-skip 55 -c 2 -f -o $O/r2f_prof_conv_80x848 \
-    python tools/profile_targets.py vqvae 16 > /dev/null 2>&1
+    python tools/profile_targets.py vqvae 64 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:attn_prefill_tc --launch-skip 3 -c 1 -f -o $O/r2f_prof_attn_prefill_tc \
     python tools/profile_targets.py prefill > /dev/null 2>&1
 compute-sanitizer --tool memcheck python tools/sanitize_targets.py gpt vqvae > $O/r2f_sanitizer_memcheck.log 2>&1
