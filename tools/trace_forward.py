@@ -26,3 +26,10 @@ tot = sum(v[1] for v in agg.values())
 for k, (n, t, _) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
     print("%-44s n=%4d total %9.1f us (%4.1f%%) avg %8.1f" % (k, n, t, 100 * t / tot, t / n))
 print("sum of kernels %.2f ms" % (tot / 1e3))
+# the four GEMMs of the layers in launch order (QKV, proj, FC1 with the GELU epilogue, FC2): per-launch durations of layers 2..4
+gem = [e for e in prof.events() if e.device_type.name == "CUDA" and "gemm_tc_persist" in e.name]
+gem.sort(key=lambda e: e.time_range.start)
+fl = [2 * 16960 * 3072 * 1024, 2 * 16960 * 1024 * 1024, 2 * 16960 * 4096 * 1024, 2 * 16960 * 1024 * 4096]
+for l in range(2, 5):
+    print("layer %d: " % l + "  ".join("%s %.1f us (%.0f TFLOP/s)" % (n, gem[4 * l + i].device_time, fl[i] / gem[4 * l + i].device_time / 1e6)
+                                       for i, n in enumerate(("QKV", "proj", "FC1", "FC2"))))
