@@ -268,7 +268,8 @@ def run_ours(a):
         mel_host.copy_(mel, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
         return x_host, mel_host, att
-    step_e2e_att()
+    keep = [step_e2e_att(), step_e2e_att()]   # two warm-up calls: the returned 288 MB pinned tensors alternate between two
+    del keep                                   # blocks of torch's caching host allocator once both exist
     barrier()
     n_att = max(1, min(a.steps, 3))
     e0.record()
