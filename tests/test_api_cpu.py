@@ -164,3 +164,49 @@ def test_melgan_dropin_state_dict_keys_and_host_errors():
         from make_golden_melgan import reference_generator
         ref = reference_generator(dict(n_mel=80, ngf=32, n_residual_layers=3), seed=3)
         assert set(ref.state_dict()) == set(sd)
+
+
+def test_parameter_signature_cache_and_its_invalidation():
+    """The wrappers decide whether libmgv's packed weight copies are stale from a signature over (data_ptr, version, device)
+    of every parameter.  The tensor list behind it is cached (walking module.parameters() costs ~1.3 ms per call with the
+    GPU idle); the cache must be rebuilt after _apply (.to / .double ...), load_state_dict and refresh_weights, in-place
+    updates must change the signature, and copy.deepcopy / pickling must not carry the cache or the handle over."""
+    import copy
+    import pickle
+    from melspec_gpt_vqvae_b200.transformer.minGPT import GPT, GPTConfig
+    from melspec_gpt_vqvae_b200.vqvae.big_model_attn_gan import LitVQVAE, _params_signature
+
+    m = LitVQVAE(128, 256)
+    sig = lambda: hash(tuple(_params_signature(x, m) for x in m._hot_modules()))
+    s0 = sig()
+    assert len(m.__dict__["_mgv_sig_tensors"]) == len(m._hot_modules()) and sig() == s0      # cached and stable
+    n_cached = sum(len(v) for v in m.__dict__["_mgv_sig_tensors"].values())
+    assert n_cached == sum(len(list(x.parameters())) + len(list(x.buffers())) for x in m._hot_modules())
+    with torch.no_grad():
+        m._decoder.conv_out.bias.add_(1.0)
+    s1 = sig()
+    assert s1 != s0, "in-place update not detected"
+    m.double()                                                                                 # _apply: new storages
+    assert m.__dict__["_mgv_sig_tensors"] == {}, "cache must be dropped by _apply"
+    s2 = sig()
+    assert s2 != s1
+    m.load_state_dict(m.state_dict())
+    assert m.__dict__["_mgv_sig_tensors"] == {}, "cache must be dropped by load_state_dict"
+    assert sig() != s2                                                                          # copy_ bumps the versions
+    sig()
+    m.refresh_weights()
+    assert m.__dict__["_mgv_sig_tensors"] == {} and m._mgv_sig is None
+    m2 = copy.deepcopy(m)
+    assert m2.__dict__["_mgv_sig_tensors"] == {} and m2._mgv_handle is None
+    m3 = pickle.loads(pickle.dumps(m))
+    assert m3.__dict__["_mgv_sig_tensors"] == {} and m3._mgv_handle is None
+
+    g = GPT(GPTConfig(128, 265, n_layer=2, n_head=4, n_embd=64))
+    a = _params_signature(g, g)
+    assert _params_signature(g, g) == a and len(g.__dict__["_mgv_sig_tensors"]) == 1
+    with torch.no_grad():
+        g.head.weight.mul_(0.5)
+    assert _params_signature(g, g) != a
+    g.float()
+    assert g.__dict__["_mgv_sig_tensors"] == {}
+    assert copy.deepcopy(g).__dict__["_mgv_sig_tensors"] == {}
