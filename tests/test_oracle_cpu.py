@@ -185,3 +185,32 @@ def test_melgan_oracle_vs_reference_golden(golden_dir):
     assert wave.shape == (2, 1, 37 * 256)
     np.testing.assert_allclose(wave.numpy(), g["wave"], atol=2e-6)
     assert float(wave.std()) > 0.05          # the fixture exercises the nonlinearity, not a flat line
+
+
+def test_upsample_phase_decomposition_is_exact():
+    """Upsample.forward (reference vqvae/big_model_attn_gan.py:182-186) = nearest 2x, then conv3x3 pad 1.  libmgv computes it
+    as four 2x2 convolutions over the LOW-res tensor (upsample_phase_weights_kernel / conv_up): output pixel (2y+py, 2x+px)
+    sees input rows {y-1, y} for py = 0 and {y, y+1} for py = 1 (same in x), with the filter rows that land on the same
+    input row summed.  This is the index rule of the kernel restated in torch fp64 against the literal form, including
+    the borders (zero padding of the upsampled image = out-of-range low-res pixels)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 6, 5, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 6, 3, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(4, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    out = torch.zeros_like(ref)
+    fold = {0: ([0], [1, 2]), 1: ([0, 1], [2])}          # phase -> filter taps folded onto low-res tap 0 and tap 1
+    for py in (0, 1):
+        for px in (0, 1):
+            wp = torch.zeros(4, 6, 2, 2, dtype=torch.float64)
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    for ky in fold[py][ty]:
+                        for kx in fold[px][tx]:
+                            wp[:, :, ty, tx] += w[:, :, ky, kx]
+            # low-res tap (ty, tx) reads input (y + ty - (1 - py), x + tx - (1 - px)): pad (1 - p) before, p after
+            xp = F.pad(x, (1 - px, px, 1 - py, py))
+            out[:, :, py::2, px::2] = F.conv2d(xp, wp, b)
+    assert torch.allclose(out, ref, atol=1e-12), (out - ref).abs().max()
