@@ -85,32 +85,71 @@ def get_codes(mel_path, device, spec_crop_len, model, transforms, folder_name='c
         print("\rfile exists:", mel_path, end="", flush=True)
 
 
-def _load_many(paths, transforms, pool):
-    """-> (good paths, float32 array (n,80,W) in [-1,1]); damaged files are reported and skipped like get_codes does"""
-    def one(p):
+def _load_slice(paths, transforms, dst, j0):
+    """worker: files paths[k] -> dst[j0 + k] (float32 (80, W) rows of the staging buffer), in place; returns the good indices"""
+    good = []
+    for k, p in enumerate(paths):
         try:
-            return p, _load_mel(p, transforms)
+            mel = transforms(np.load(p))
+            row = dst[j0 + k]
+            np.multiply(mel, 2, out=row, casting="unsafe")   # 2 * mel - 1 (reference :43), written where the GPU copy reads it
+            row -= 1
+            good.append(j0 + k)
         except Exception:
             print(p, "is damaged")
-            return p, None
-    res = [r for r in pool.map(one, paths) if r[1] is not None]
-    if not res:
-        return [], None
-    return [r[0] for r in res], np.stack([r[1] for r in res])
+    return good
+
+
+def _load_many(paths, transforms, pool, dst, n_workers):
+    """Loads a batch straight into `dst` (numpy view of a pinned staging buffer, (>= len(paths), 80, W)).  The batch is cut into
+    one contiguous slice per worker: a task per FILE through a 16-thread pool ran at 1 100 files/s (GIL hand-offs, np.stack and
+    a second copy into the staging buffer) where one thread alone loads 5 000 files/s.  -> (good paths, their rows in dst);
+    damaged files are reported and skipped like get_codes does"""
+    n = len(paths)
+    per = (n + n_workers - 1) // n_workers
+    futs = [pool.submit(_load_slice, paths[a:a + per], transforms, dst, a) for a in range(0, n, per)]
+    rows = [j for f in futs for j in f.result()]
+    return [paths[j] for j in rows], rows
+
+
+_NPY_HEADERS = {}
+_MADE_DIRS = set()
 
 
 def _save_code(out, codes):
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    np.save(out, codes)
+    """np.save(out, codes) for the small code grids, without its per-call header formatting: the .npy header of a
+    (shape, dtype) is built once by numpy itself and reused, so the files are byte-identical to np.save's."""
+    d = os.path.dirname(out)
+    if d not in _MADE_DIRS:
+        os.makedirs(d, exist_ok=True)
+        _MADE_DIRS.add(d)
+    codes = np.ascontiguousarray(codes)
+    key = (codes.shape, codes.dtype.str)
+    hdr = _NPY_HEADERS.get(key)
+    if hdr is None:
+        import io
+        bio = io.BytesIO()
+        np.save(bio, np.zeros(codes.shape, codes.dtype))
+        raw = bio.getvalue()
+        hdr = _NPY_HEADERS[key] = raw[:len(raw) - codes.nbytes]
+    try:
+        f = open(out, "wb")
+    except FileNotFoundError:      # the directory disappeared since it was last seen
+        os.makedirs(d, exist_ok=True)
+        f = open(out, "wb")
+    with f:
+        f.write(hdr)
+        f.write(codes.tobytes())
 
 
 def get_codes_batch(mel_paths, device, spec_crop_len, model, transforms, folder_name='codes_10s', batch_size=64,
                     io_threads=8):
     """Batched walk with the same per-file results as calling get_codes on each path.
 
-    Three overlapped stages so that the encoder (~3 000 clips/s on one B200) is not I/O-bound: a thread pool loads
-    and crops the next batch of `*_mel.npy` files while the GPU works on the current one, batches go through a
-    pinned host staging buffer with an asynchronous copy, and the (5,53) int64 code files are written by the pool."""
+    Three overlapped stages so that the encoder (~4 600 clips/s on one B200) is not I/O-bound: the next batch of
+    `*_mel.npy` files is loaded, cropped and scaled straight into a pinned staging buffer (a few contiguous slices per
+    batch, one worker each) while the GPU works on the current one, the copy to the device is asynchronous, and the
+    (5,53) int64 code files are written by the pool (byte-identical to np.save's)."""
     from concurrent.futures import ThreadPoolExecutor
     todo = [p for p in mel_paths if not os.path.isfile(_out_path(p, folder_name))]
     if not todo:
@@ -118,22 +157,34 @@ def get_codes_batch(mel_paths, device, spec_crop_len, model, transforms, folder_
     chunks = [todo[i:i + batch_size] for i in range(0, len(todo), batch_size)]
     done = 0
     writes = []
-    staging = [None, None]                       # two pinned buffers: batch i+1 is staged while batch i is in flight
+    n_workers = max(1, min(io_threads, 4))       # loader slices per batch (more threads only add GIL hand-offs)
+    probe = None                                  # crop shape of this walk (every file is cropped to the same shape)
+    for p in todo:
+        try:
+            probe = transforms(np.load(p))
+            break
+        except Exception:
+            continue
+    if probe is None:
+        for p in todo:
+            print(p, "is damaged")
+        return 0
+    shape = (batch_size,) + tuple(probe.shape)
+    # two pinned buffers: batch i+1 is loaded (by the pool, straight into its buffer) while batch i is in flight
+    staging = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+    views = [b.numpy() for b in staging]
     with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool, ThreadPoolExecutor(max_workers=1) as prefetch:
-        nxt = prefetch.submit(_load_many, chunks[0], transforms, pool)
+        nxt = prefetch.submit(_load_many, chunks[0], transforms, pool, views[0], n_workers)
         for i in range(len(chunks)):
-            chunk, mels = nxt.result()
+            chunk, rows = nxt.result()
             if i + 1 < len(chunks):
-                nxt = prefetch.submit(_load_many, chunks[i + 1], transforms, pool)
+                nxt = prefetch.submit(_load_many, chunks[i + 1], transforms, pool, views[(i + 1) & 1], n_workers)
             if not chunk:
                 continue
             try:
                 buf = staging[i & 1]
-                if buf is None or buf.shape[0] < mels.shape[0] or buf.shape[1:] != mels.shape[1:]:
-                    buf = staging[i & 1] = torch.empty((max(batch_size, mels.shape[0]),) + mels.shape[1:],
-                                                       dtype=torch.float32).pin_memory()
-                buf[:mels.shape[0]].copy_(torch.from_numpy(mels))
-                codes = encode_batch(buf[:mels.shape[0]], device, model)
+                mels = buf[:len(chunks[i])] if len(rows) == len(chunks[i]) else buf[torch.as_tensor(rows)].pin_memory()
+                codes = encode_batch(mels, device, model)
             except Exception:
                 for p in chunk:
                     print(p, "is damaged")
