@@ -210,3 +210,42 @@ def test_parameter_signature_cache_and_its_invalidation():
     g.float()
     assert g.__dict__["_mgv_sig_tensors"] == {}
     assert copy.deepcopy(g).__dict__["_mgv_sig_tensors"] == {}
+
+
+def test_extract_codes_loader_and_writer_host_logic(tmp_path):
+    """Host stages of the batched extract_codes walk (no GPU): a batch is loaded straight into the staging buffer with the
+    reference's `2 * crop(mel) - 1` (feature_extraction/extract_codes.py:40-43 of the reference), damaged files are reported
+    and skipped, and the code files are byte-identical to what np.save writes (reference :58)."""
+    import io
+    from concurrent.futures import ThreadPoolExecutor
+    from melspec_gpt_vqvae_b200.feature_extraction import extract_codes as ec
+    d = tmp_path / "cls" / "melspec_10s_22050hz"
+    d.mkdir(parents=True)
+    rng = np.random.default_rng(1)
+    paths = []
+    for i in range(7):
+        p = str(d / ("clip%02d_mel.npy" % i))
+        arr = rng.random((80, 860)).astype(np.float64 if i == 2 else np.float32)       # one float64 file
+        np.save(p, arr)
+        paths.append(p)
+    (d / "broken_mel.npy").write_bytes(b"not a numpy file")
+    np.save(str(d / "short_mel.npy"), rng.random((80, 100), dtype=np.float32))          # narrower than the crop
+    bad = [str(d / "broken_mel.npy"), str(d / "short_mel.npy")]
+    tr = ec.Crop([80, 848], False)
+    batch = paths[:3] + [bad[0]] + paths[3:5] + [bad[1]] + paths[5:]
+    dst = np.full((len(batch), 80, 848), np.nan, dtype=np.float32)
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        good, rows = ec._load_many(batch, tr, pool, dst, 3)
+    assert good == paths and rows == [0, 1, 2, 4, 5, 7, 8]
+    for p, j in zip(good, rows):
+        ref = 2 * tr(np.load(p).astype(np.float32)) - 1
+        assert np.array_equal(dst[j], ref), p
+    codes = rng.integers(0, 128, (5, 53)).astype(np.int64)
+    out = ec._out_path(paths[0], "codes_10s")
+    assert out.endswith(os.path.join("cls", "codes_10s", "clip00_mel_code.npy"))
+    ec._save_code(out, codes)
+    ref = io.BytesIO()
+    np.save(ref, codes)
+    assert open(out, "rb").read() == ref.getvalue()
+    ec._save_code(out, codes.astype(np.int32).T)                                         # another shape / dtype: its own header
+    assert np.array_equal(np.load(out), codes.astype(np.int32).T)
