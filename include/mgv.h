@@ -189,7 +189,14 @@ int mgv_vqvae_load_weight(mgv_vqvae_t* v, const char* name, const float* src, in
 
 /* Lit_minGPT.decode_to_img after code_reader (transformer/minGPT.py:515-528):
  * get_codebook_entry + post_quant_conv + Decoder.forward (big_model_attn_gan.py:56-71,
- * :610-614, :361-392).  idx: int64 (B, H*W) row-major code grid; mel_out: fp32 (B,1,80,848). */
+ * :610-614, :361-392).  idx: int64 (B, H*W) row-major code grid; mel_out: fp32 (B,1,80,848).
+ * Returns after `stream` has completed (the out-of-range index flag is read back).  From the second
+ * call at a batch size on, the ~150 launches are captured into / replayed from a CUDA graph owned by
+ * the handle: idx and mel_out are copied through handle-owned staging buffers on `stream`, so the
+ * call stays stream-ordered and the caller's pointers may change from call to call; weights loaded
+ * later are seen by the graph (they are rewritten in place).  One call at a time per handle.
+ * Upsample (:182-186) is evaluated as four 2x2 convolutions over the low-res tensor (same result up
+ * to the bf16 rounding of the pre-summed weights). */
 int mgv_vqvae_decode_codes(mgv_vqvae_t* v, const int64_t* idx, int B, float* mel_out, mgv_stream_t stream);
 
 /* LitVQVAE.decode(quant) (:610-614): quant fp32 (B, 256, 5, 53) BCHW -> mel (B,1,80,848). */
