@@ -43,3 +43,19 @@ def test_sharding_and_timing_reduction_world2():
     assert gathered[0] + gathered[1] == ["clip%03d" % i for i in range(11)]
     assert set(gathered[0]).isdisjoint(gathered[1])
     assert t == 11.0 and seed0 == 783435
+
+
+def test_bench_roofline_arithmetic_matches_survey_figures():
+    """bench.py's algorithmic bytes of the decode loop against SURVEY section 8(d) / BASELINE.md section 4: 604.9 MB of bf16
+    weights per position, 98 304 B of KV per sequence and context position, ~382 GB per 64 clips of 265 tokens."""
+    import bench
+    from melspec_gpt_vqvae_b200 import synthetic
+    cfg = synthetic.GPT_VAS
+    one = bench.decode_algorithmic_bytes(1, 1, cfg)
+    C, L, V = cfg["n_embd"], cfg["n_layer"], cfg["vocab_size"]
+    weights = (L * 12 * C * C + V * C) * 2
+    assert abs(weights / 1e6 - 604.9) < 1.0          # 604.2 MB of Linear weights (SURVEY rounds in the embeddings)
+    assert one == weights + 98304
+    total = bench.decode_algorithmic_bytes(64, 265, cfg)
+    assert total == 265 * weights + 64 * 98304 * (265 * 266 // 2)
+    assert abs(total / 1e9 - 381.9) < 0.2
